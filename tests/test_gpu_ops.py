@@ -1,0 +1,303 @@
+"""Per-kernel parity: every sm_100a kernel, called through the C ABI, against plain PyTorch fp32 math
+on the same seeded inputs.  Tolerances: fp32 kernels 1e-4 relative-to-scale; bf16 kernels are compared
+with an fp32 reference computed from the same bf16-rounded inputs and must agree to bf16 output
+rounding (2^-8 relative to the tensor scale)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1.0 / 128  # output rounding (2^-9) + accumulation-order slack, relative to max|ref|
+F32_TOL = 2e-5
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda")
+
+
+def _close(out, ref, tol, what=""):
+    out = out.float()
+    ref = ref.float()
+    assert out.shape == ref.shape, f"{what}: shape {tuple(out.shape)} vs {tuple(ref.shape)}"
+    assert torch.isfinite(out).all(), f"{what}: non-finite output"
+    scale = ref.abs().max().item() + 1e-12
+    err = (out - ref).abs().max().item() / scale
+    assert err <= tol, f"{what}: max err {err:.3e} of scale {scale:.3e} exceeds {tol:.1e}"
+
+
+def _act_ref(x, act):
+    if act == 1:
+        return F.gelu(x)
+    if act == 2:
+        return F.silu(x)
+    if act == 3:
+        return F.relu(x)
+    return x
+
+
+GEMM_SHAPES = [
+    # M, N, K                       what it stands for
+    (128, 128, 64),                 # single tile
+    (256, 256, 128),
+    (300, 96, 96),                  # M/N/K tails (stage-0 fc2: K=4*96... here K=96 partial k-block)
+    (1000, 192, 384),               # stage-1 fc2 shape, ragged M
+    (544, 1152, 896),               # Qwen2-0.5B fused qkv, M = 2 x 272
+    (4096, 1536, 384),              # stage-2 fc1
+    (1024, 2304, 768),              # stage-3 qkv
+    (77, 896, 3072),                # projector, tiny ragged M
+    (20000, 384, 96),               # many tiles per CTA (persistent loop, both accumulator stages)
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", ["plain", "bias_gelu", "bias_resid", "silu_rowscale"])
+def test_gemm_bf16(native, M, N, K, epi):
+    dev = _dev()
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev) if epi != "plain" else None
+    resid = torch.randn(M, N, generator=g).to(dev).bfloat16() if epi == "bias_resid" else None
+    rs = (torch.rand(M, generator=g) + 0.5).to(dev) if epi == "silu_rowscale" else None
+    act = {"plain": 0, "bias_gelu": 1, "bias_resid": 0, "silu_rowscale": 2}[epi]
+    out = native.op_gemm(a, w, bias=bias, resid=resid, act=act, row_scale=rs)
+    ref = a.float() @ w.float().t()
+    if rs is not None:
+        ref = ref * rs[:, None]
+    if bias is not None:
+        ref = ref + bias
+    ref = _act_ref(ref, act)
+    if resid is not None:
+        ref = ref + resid.float()
+    _close(out, ref, BF16_TOL, f"gemm bf16 {M}x{N}x{K} {epi}")
+
+
+@pytest.mark.parametrize("bn", [64, 128, 192, 256])
+def test_gemm_bf16_every_tile_width(native, bn):
+    dev = _dev()
+    g = torch.Generator().manual_seed(bn)
+    M, N, K = 777, 448, 320
+    a = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    out = native.op_gemm(a, w, bias=bias, block_n=bn)
+    _close(out, a.float() @ w.float().t() + bias, BF16_TOL, f"gemm bn={bn}")
+
+
+def test_gemm_bf16_inplace_residual(native):
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 640, 384, 1536
+    a = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    x = torch.randn(M, N, generator=g).to(dev).bfloat16()
+    ref = a.float() @ w.float().t() + x.float()
+    out = native.op_gemm(a, w, resid=x, out=x)
+    assert out.data_ptr() == x.data_ptr()
+    _close(out, ref, BF16_TOL, "gemm in-place residual")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,I,K", [(272, 4864, 896), (100, 256, 128), (1000, 640, 64)])
+def test_gemm_swiglu(native, dtype, M, I, K):
+    dev = _dev()
+    g = torch.Generator().manual_seed(I + K)
+    a = torch.randn(M, K, generator=g).to(dev).to(dtype)
+    gate = (torch.randn(I, K, generator=g) / math.sqrt(K)).to(dev).to(dtype)
+    up = (torch.randn(I, K, generator=g) / math.sqrt(K)).to(dev).to(dtype)
+    w = torch.stack([gate, up], dim=1).reshape(2 * I, K).contiguous()  # rows: g0,u0,g1,u1,...
+    out = native.op_gemm(a, w, swiglu=True)
+    ref = F.silu(a.float() @ gate.float().t()) * (a.float() @ up.float().t())
+    _close(out, ref, BF16_TOL if dtype == torch.bfloat16 else F32_TOL, f"swiglu {dtype}")
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 96, 96), (513, 200, 72), (128, 64, 16), (1000, 1152, 896)])
+@pytest.mark.parametrize("epi", ["plain", "bias_gelu", "bias_resid", "silu_rowscale"])
+def test_gemm_f32(native, M, N, K, epi):
+    dev = _dev()
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev)
+    bias = torch.randn(N, generator=g).to(dev) if epi != "plain" else None
+    resid = torch.randn(M, N, generator=g).to(dev) if epi == "bias_resid" else None
+    rs = (torch.rand(M, generator=g) + 0.5).to(dev) if epi == "silu_rowscale" else None
+    act = {"plain": 0, "bias_gelu": 1, "bias_resid": 0, "silu_rowscale": 2}[epi]
+    out = native.op_gemm(a, w, bias=bias, resid=resid, act=act, row_scale=rs)
+    ref = a.double() @ w.double().t()
+    if rs is not None:
+        ref = ref * rs[:, None].double()
+    if bias is not None:
+        ref = ref + bias.double()
+    ref = _act_ref(ref, act)
+    if resid is not None:
+        ref = ref + resid.double()
+    _close(out, ref.float(), F32_TOL, f"gemm f32 {M}x{N}x{K} {epi}")
+
+
+def _pack_dw(w):  # [Cout,1,k,k] -> [k*k][Cout]
+    cout, _, k, _ = w.shape
+    return w.reshape(cout, k * k).t().contiguous()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("k,stride,mult,act", [(3, 1, 1, 0), (3, 2, 1, 1), (7, 1, 1, 0), (7, 2, 2, 1),
+                                               (3, 1, 2, 0), (7, 2, 1, 0)])
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 16), (1, 37, 29, 24), (3, 64, 64, 96)])
+def test_dwconv(native, dtype, k, stride, mult, act, B, H, W, C):
+    dev = _dev()
+    if stride == 2 and (H % 2 or W % 2):
+        H, W = H + H % 2, W + W % 2
+    g = torch.Generator().manual_seed(k * 100 + stride * 10 + mult + C)
+    x = torch.randn(B, C, H, W, generator=g).to(dev)
+    w = (torch.randn(C * mult, 1, k, k, generator=g) / k).to(dev)
+    b = torch.randn(C * mult, generator=g).to(dev)
+    xin = x.permute(0, 2, 3, 1).contiguous().to(dtype)
+    out = native.op_dwconv(xin, _pack_dw(w), b, k, stride, mult, act)
+    ref = F.conv2d(xin.float().permute(0, 3, 1, 2), w, b, stride=stride, padding=k // 2, groups=C)
+    ref = _act_ref(ref, act).permute(0, 2, 3, 1)
+    _close(out, ref, BF16_TOL if dtype == torch.bfloat16 else F32_TOL, f"dwconv k{k}s{stride}m{mult}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stem_conv(native, dtype):
+    dev = _dev()
+    g = torch.Generator().manual_seed(11)
+    B, H, W, Cout = 2, 64, 48, 96
+    x = torch.rand(B, 3, H, W, generator=g).to(dev)
+    w = (torch.randn(Cout, 3, 3, 3, generator=g) / 3).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    x4 = torch.zeros(B, H, W, 4, device=dev)
+    x4[..., :3] = x.permute(0, 2, 3, 1)
+    x4 = x4.to(dtype)
+    wp = w.permute(2, 3, 1, 0).reshape(27, Cout).contiguous()  # row = (ky*3+kx)*3+ci
+    out = native.op_stem_conv(x4, wp, b)
+    ref = F.gelu(F.conv2d(x4[..., :3].float().permute(0, 3, 1, 2), w, b, stride=2, padding=1)).permute(0, 2, 3, 1)
+    _close(out, ref, BF16_TOL if dtype == torch.bfloat16 else F32_TOL, "stem conv")
+
+
+def _resize_with_pad_ref(img, S, pad_value=0.0):
+    # restates fastvlm_adapter.py:36-55
+    h, w = img.shape[2:]
+    ratio = max(w / S, h / S)
+    rh, rw = int(h / ratio), int(w / ratio)
+    r = F.interpolate(img, size=(rh, rw), mode="bilinear", align_corners=False)
+    return F.pad(r, (max(0, S - rw), 0, max(0, S - rh), 0), value=pad_value)
+
+
+@pytest.mark.parametrize("shape,S", [((2, 3, 480, 480), 1024), ((1, 3, 480, 640), 1024), ((2, 3, 64, 64), 64),
+                                     ((1, 1, 50, 70), 128), ((1, 4, 300, 200), 256), ((1, 3, 1500, 1100), 512)])
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_preprocess_letterbox(native, shape, S, nhwc):
+    dev = _dev()
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.rand(*shape, generator=g).to(dev)
+    xc = x.repeat(1, 3, 1, 1) if shape[1] == 1 else x[:, :3]
+    ref = _resize_with_pad_ref(xc, S, 0.25).permute(0, 2, 3, 1)
+    src = x.permute(0, 2, 3, 1).contiguous() if nhwc else x
+    out = native.op_preprocess(src, S, torch.float32, nhwc=nhwc, letterbox=True, pad_value=0.25)
+    _close(out[..., :3], ref, 1e-5, f"preprocess {shape}->{S}")
+    assert (out[..., 3] == 0).all()
+
+
+def test_preprocess_uint8_stretch_and_normalize(native):
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 256, (2, 3, 40, 60), generator=g, dtype=torch.uint8).to(dev)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    out = native.op_preprocess(x, 96, torch.float32, letterbox=False, scale=1 / 255.0, mean=mean, std=std)
+    ref = F.interpolate(x.float(), size=(96, 96), mode="bilinear", align_corners=False) / 255.0
+    ref = (ref - torch.tensor(mean, device=dev).view(1, 3, 1, 1)) / torch.tensor(std, device=dev).view(1, 3, 1, 1)
+    _close(out[..., :3], ref.permute(0, 2, 3, 1), 1e-5, "preprocess u8")
+
+
+def _rope_tables(T, hd, theta, dev):
+    inv = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
+    ang = torch.arange(T, dtype=torch.float32)[:, None] * inv[None, :]
+    return ang.cos().to(dev).contiguous(), ang.sin().to(dev).contiguous()
+
+
+def _attn_ref(qkv, B, N, hq, hkv, hd, scale, causal, cos=None, sin=None):
+    qkv = qkv.float().view(B, N, -1)
+    q = qkv[..., : hq * hd].view(B, N, hq, hd).transpose(1, 2)
+    k = qkv[..., hq * hd: (hq + hkv) * hd].view(B, N, hkv, hd).transpose(1, 2)
+    v = qkv[..., (hq + hkv) * hd:].view(B, N, hkv, hd).transpose(1, 2)
+    if cos is not None:
+        c = torch.cat([cos, cos], -1)[None, None]
+        s = torch.cat([sin, sin], -1)[None, None]
+
+        def rot(x):
+            x1, x2 = x[..., : hd // 2], x[..., hd // 2:]
+            return x * c + torch.cat([-x2, x1], -1) * s
+
+        q, k = rot(q), rot(k)
+    k = k.repeat_interleave(hq // hkv, dim=1)
+    v = v.repeat_interleave(hq // hkv, dim=1)
+    att = (q @ k.transpose(-1, -2)) * scale
+    if causal:
+        att = att.masked_fill(torch.ones(N, N, device=att.device, dtype=torch.bool).triu(1), float("-inf"))
+    o = att.softmax(-1) @ v
+    return o.transpose(1, 2).reshape(B * N, hq * hd)
+
+
+ATTN_CASES = [
+    # B, N, hq, hkv, hd, causal, rope
+    (2, 1024, 24, 24, 32, False, False),   # FastViTHD stage 3
+    (3, 256, 48, 48, 32, False, False),    # FastViTHD stage 4
+    (2, 272, 14, 2, 64, True, True),       # Qwen2-0.5B prefill, T' = 256 + 16
+    (2, 100, 12, 2, 128, True, True),      # Qwen2-1.5B / 7B head_dim
+    (1, 77, 4, 4, 32, False, False),       # ragged N
+    (2, 19, 2, 1, 64, True, True),         # tiny test-model shape
+]
+
+
+@pytest.mark.parametrize("B,N,hq,hkv,hd,causal,rope", ATTN_CASES)
+@pytest.mark.parametrize("impl,dtype", [(0, torch.bfloat16), (1, torch.bfloat16), (0, torch.float32)])
+def test_attention(native, B, N, hq, hkv, hd, causal, rope, impl, dtype):
+    dev = _dev()
+    g = torch.Generator().manual_seed(N + hd)
+    qkv = torch.randn(B * N, (hq + 2 * hkv) * hd, generator=g).to(dev).to(dtype)
+    cos = sin = None
+    if rope:
+        cos, sin = _rope_tables(N, hd, 1e6, dev)
+    scale = hd ** -0.5
+    out = native.op_attention(qkv, B, N, hq, hkv, hd, scale, causal, cos, sin, impl=impl)
+    ref = _attn_ref(qkv, B, N, hq, hkv, hd, scale, causal, cos, sin)
+    # flash path rounds P and the rotated q/k to bf16: allow 2x the plain bf16 tolerance
+    tol = 2 * BF16_TOL if dtype == torch.bfloat16 else 1e-4
+    _close(out, ref, tol, f"attention impl={impl} {dtype}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_rmsnorm(native, dtype):
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    x = (torch.randn(333, 896, generator=g) * 3).to(dev).to(dtype)
+    w = torch.randn(896, generator=g).to(dev)
+    out = native.op_rmsnorm(x, w, 1e-6)
+    xf = x.float()
+    ref = w * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6))
+    _close(out, ref, BF16_TOL if dtype == torch.bfloat16 else F32_TOL, "rmsnorm")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_se_gelu(native, dtype):
+    dev = _dev()
+    g = torch.Generator().manual_seed(21)
+    B, HW, Cc, Cr = 3, 256, 512, 32
+    x = torch.randn(B, HW, Cc, generator=g).to(dev).to(dtype)
+    w1 = (torch.randn(Cr, Cc, generator=g) / math.sqrt(Cc)).to(dev)
+    b1 = torch.randn(Cr, generator=g).to(dev)
+    w2 = (torch.randn(Cc, Cr, generator=g) / math.sqrt(Cr)).to(dev)
+    b2 = torch.randn(Cc, generator=g).to(dev)
+    out = native.op_se_gelu(x, w1, b1, w2, b2)
+    xf = x.float()
+    gate = torch.sigmoid(F.relu(xf.mean(1) @ w1.t() + b1) @ w2.t() + b2)
+    ref = F.gelu(xf * gate[:, None, :])
+    _close(out, ref, BF16_TOL if dtype == torch.bfloat16 else F32_TOL, "se_gelu")

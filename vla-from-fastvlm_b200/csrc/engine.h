@@ -1,0 +1,117 @@
+// FastVLA forward engine: owns packed weights + workspace and sequences the sm_100a kernels for
+// FastViTHD -> mm_projector -> LLaVA splice -> Qwen2 prefill -> pooling -> action head.
+#pragma once
+#include "../../include/fvla.h"
+#include "kernels.h"
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace fvla {
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const { int64_t n = 1; for (auto d : shape) n *= d; return n; }
+};
+
+struct GemmW {  // packed nn.Linear / 1x1 conv
+  void* w = nullptr;          // [N, K] in engine dtype
+  const float* bias = nullptr;  // [N] fp32 or null
+  int N = 0, K = 0;
+};
+struct DwW {  // packed depthwise / grouped conv
+  float* w = nullptr;     // [k*k][Cout] fp32
+  float* bias = nullptr;  // [Cout] fp32
+  int cin = 0, mult = 1, k = 3, stride = 1, act = 0;
+};
+struct VisBlock {
+  bool attn = false;
+  DwW mixer;           // RepMixer reparam 3x3 (repmixer blocks only)
+  GemmW qkv, proj;     // attention blocks only (BN folded into qkv, layer_scale_1 into proj)
+  DwW ffn_dw;          // ConvFFN 7x7 with BN folded
+  GemmW fc1, fc2;      // fc2 carries the folded layer scale
+};
+struct VisStage {
+  int dim = 0;
+  bool has_cpe = false; DwW cpe;
+  std::vector<VisBlock> blocks;
+  bool has_down = false; DwW down_dw; GemmW down_pw;
+};
+struct DecLayer {
+  float* ln1 = nullptr; float* ln2 = nullptr;
+  GemmW qkv, o, gate_up, down;
+};
+
+struct Workspace {
+  std::map<std::string, std::pair<void*, size_t>> bufs;
+  size_t total = 0;
+};
+
+class Engine {
+ public:
+  explicit Engine(const fvla_config& cfg);
+  ~Engine();
+  int load_tensor(const char* name, const void* data, int dtype, int ndim, const int64_t* shape);
+  int missing(std::vector<std::string>* out);
+  int finalize();
+  int reserve(int B, int n_tokens);
+  int forward(const fvla_forward_args& a, cudaStream_t stream);
+  int set_tap(int stage, void* dst, int64_t cap);
+
+  fvla_config cfg;
+  int64_t launches = 0;
+  double flops = 0.0;
+  int merged_len = 0;
+  size_t weight_bytes = 0;
+  size_t workspace_bytes() const { return ws_.total; }
+
+ private:
+  std::vector<std::string> required_names() const;
+  const HostTensor* find(const std::string& name) const;
+  int need(const std::string& name, const HostTensor** out, std::initializer_list<int64_t> shape);
+
+  float* upload_f32(const std::vector<float>& v);
+  void* upload_act(const std::vector<float>& v);  // engine dtype
+  int make_gemm(GemmW* g, const std::vector<float>& w, int N, int K, const std::vector<float>* bias);
+  int make_dw(DwW* d, const std::vector<float>& w_oihw, const std::vector<float>& bias, int cin,
+              int mult, int k, int stride, int act);
+  int pack_vision();
+  int pack_decoder();
+  int pack_head();
+
+  int ensure(const std::string& name, size_t bytes, void** out);
+  int tap(int stage, const void* src, size_t bytes, size_t dst_offset_bytes, cudaStream_t s);
+
+  int run_gemm(const GemmW& w, const void* A, void* D, int M, int act, const void* resid, bool swiglu,
+               cudaStream_t s);
+  int run_dw(const DwW& w, const void* in, void* out, int B, int H, int W, cudaStream_t s);
+  int vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats, cudaStream_t s);
+
+  size_t esz() const { return dtype_size(cfg.dtype); }
+  int n_img_tokens() const;
+  int mm_hidden() const;
+
+  std::map<std::string, HostTensor> host_;
+  bool finalized_ = false;
+  std::vector<void*> dev_allocs_;
+
+  // packed model
+  float* stem0_w_ = nullptr; float* stem0_b_ = nullptr;
+  DwW stem1_; GemmW stem2_;
+  std::vector<VisStage> stages_;
+  DwW exp_dw_;
+  float *se_w1_ = nullptr, *se_b1_ = nullptr, *se_w2_ = nullptr, *se_b2_ = nullptr;
+  GemmW proj0_, proj2_;
+  void* embed_ = nullptr;
+  std::vector<DecLayer> layers_;
+  float* final_norm_ = nullptr;
+  float* rope_cos_ = nullptr; float* rope_sin_ = nullptr; int rope_len_ = 0;
+  HeadWeights head_{};
+
+  Workspace ws_;
+  std::map<int, std::pair<void*, int64_t>> taps_;
+};
+
+}  // namespace fvla

@@ -1,0 +1,419 @@
+// bf16 GEMM for sm_100a:  D[M,N] = epilogue( A[M,K] * W[N,K]^T )
+//
+// This is the 1x1-conv / nn.Linear workhorse of the FastVLA forward (FastViTHD ConvFFN fc1/fc2,
+// patch-embed pointwise convs, MHSA qkv/proj, mm_projector, Qwen2 q/k/v/o/gate/up/down).
+// Activations are NHWC / token-major, so A is row-major [M, K]; torch keeps Linear and 1x1-conv
+// weights as [N, K] — both operands are K-major and go to the tensor core untouched.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0     TMA producer: A/W tiles -> 128B-swizzled shared memory ring (mbarrier full/empty)
+//   warp 1     MMA issuer: one thread issues tcgen05.mma (128 x BLOCK_N x 16), accumulators in TMEM,
+//              two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warp 2     TMEM allocator
+//   warps 4-7  epilogue: tcgen05.ld -> row-scale / bias / activation / residual / SwiGLU -> bf16 ->
+//              swizzled staging tile -> TMA store (bounds clipped by the tensor map)
+//
+// Edges need no special code: TMA zero-fills out-of-bounds loads (M, N and K tails) and clips stores.
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "kernels.h"
+
+#include <mutex>
+
+namespace fvla {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int EPI_THREADS = 128;
+constexpr int STAGING_BYTES = BLOCK_M * 64 * 2;  // 128 rows x 64 bf16 output columns
+
+template <int BLOCK_N> struct GemmCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N >= 192) ? 4 : (BLOCK_N == 128 ? 5 : 6);
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGING_BYTES + BAR_BYTES + 1024;
+};
+
+struct EpiParams {
+  int M, N, K;
+  const float* bias;           // [N] or null
+  const float* row_scale;      // [M] or null (applied to the accumulator before the bias)
+  const __nv_bfloat16* resid;  // [M, ldr] or null (added after the activation)
+  int ldr;
+  int act;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BLOCK_N, bool SWIGLU>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_w,
+                         const __grid_constant__ CUtensorMap tmap_d, const EpiParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  // accumulator columns consumed per 64-column output sub-tile
+  constexpr int ACC_PER_SUB = SWIGLU ? 128 : 64;
+  static_assert(BLOCK_N % ACC_PER_SUB == 0, "BLOCK_N must cover whole output sub-tiles");
+  constexpr int NUM_SUB = BLOCK_N / ACC_PER_SUB;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_b0 = smem_base + STAGES * Cfg::A_BYTES;
+  const uint32_t smem_stage0 = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = smem_stage0 + 2 * STAGING_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_w);
+    ptx::prefetch_tmap(&tmap_d);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), EPI_THREADS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BLOCK_M;
+        const int n0 = (tile % num_n) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          ptx::tma_load_2d(smem_a0 + stage * Cfg::A_BYTES, &tmap_a, kb * BLOCK_K, m0,
+                           full_bar(stage));
+          ptx::tma_load_2d(smem_b0 + stage * Cfg::B_BYTES, &tmap_w, kb * BLOCK_K, n0,
+                           full_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::make_kmajor_sw128_desc(smem_a0 + stage * Cfg::A_BYTES);
+          const uint64_t db = ptx::make_kmajor_sw128_desc(smem_b0 + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B inside the swizzle row: +2 in the (addr >> 4) field
+            ptx::umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k),
+                           db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          if (kb == num_kb - 1) ptx::umma_commit(tfull_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue =====================
+    const int epi_tid = threadIdx.x - 128;  // == tile row == TMEM lane
+    const int ew = warp_idx - 4;            // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int sbuf = 0;
+    const int n_out_total = SWIGLU ? p.N / 2 : p.N;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * BLOCK_M;
+      const int n0 = (tile % num_n) * BLOCK_N;
+      const int m = m0 + epi_tid;
+      const bool row_ok = m < p.M;
+      float rs = 1.0f;
+      if (p.row_scale != nullptr && row_ok) rs = __ldg(p.row_scale + m);
+
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t tmem_acc =
+          tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+
+#pragma unroll 1
+      for (int sub = 0; sub < NUM_SUB; ++sub) {
+        const int acc_col0 = sub * ACC_PER_SUB;                 // first accumulator column
+        const int out_col0 = (SWIGLU ? (n0 / 2) : n0) + sub * 64;  // first output column
+        if (out_col0 >= n_out_total) break;                     // whole sub-tile out of range
+        // the TMA store issued from this staging buffer two sub-tiles ago must have read it
+        if (epi_tid == 0) ptx::tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t sbase = smem_stage0 + sbuf * STAGING_BYTES + epi_tid * 128;
+
+#pragma unroll
+        for (int q = 0; q < ACC_PER_SUB / 32; ++q) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(acc_col0 + q * 32), r);
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rs;
+
+          if constexpr (SWIGLU) {
+            // columns are (gate, up) pairs: 32 accumulators -> 16 outputs
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a0 = silu_precise(v[4 * j]) * v[4 * j + 1];
+              const float a1 = silu_precise(v[4 * j + 2]) * v[4 * j + 3];
+              o[j] = pack_bf16(a0, a1);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int chunk = 2 * q + c;
+              const uint32_t dst = sbase + ((chunk ^ (epi_tid & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[4 * c]),
+                           "r"(o[4 * c + 1]), "r"(o[4 * c + 2]), "r"(o[4 * c + 3])
+                           : "memory");
+            }
+          } else {
+            const int nb = n0 + acc_col0 + q * 32;  // global column of v[0]
+            if (p.bias != nullptr) {
+              if (nb + 32 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j);
+                  v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
+              }
+            }
+            if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            } else if (p.act == ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu_precise(v[j]);
+            }
+            if (p.resid != nullptr && row_ok) {
+              const __nv_bfloat16* rp = p.resid + static_cast<size_t>(m) * p.ldr + nb;
+              if (nb + 32 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+                  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    v[8 * j + 2 * t] += __uint_as_float(w[t] << 16);
+                    v[8 * j + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (nb + j < p.N) v[j] += __bfloat162float(rp[j]);
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int chunk = 4 * q + c;
+              const uint32_t dst = sbase + ((chunk ^ (epi_tid & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                           "r"(pack_bf16(v[8 * c], v[8 * c + 1])),
+                           "r"(pack_bf16(v[8 * c + 2], v[8 * c + 3])),
+                           "r"(pack_bf16(v[8 * c + 4], v[8 * c + 5])),
+                           "r"(pack_bf16(v[8 * c + 6], v[8 * c + 7]))
+                           : "memory");
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (epi_tid == 0) {
+          ptx::tma_store_2d(&tmap_d, out_col0, m0, smem_stage0 + sbuf * STAGING_BYTES);
+          ptx::tma_store_commit();
+        }
+        sbuf ^= 1;
+      }
+      // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (epi_tid == 0) ptx::tma_store_wait<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---- host side: tensor maps + launch --------------------------------------------------------
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row pitch ld (elements); box = box_rows x 64 cols, 128B swizzle.
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld,
+                   int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  FVLA_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  FVLA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "TMA base must be 16-byte aligned");
+  FVLA_REQUIRE((ld * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 1;
+  }
+  return 0;
+}
+
+template <int BLOCK_N, bool SWIGLU>
+int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  auto kfn = gemm_bf16_tcgen05_kernel<BLOCK_N, SWIGLU>;
+  if (!attr_set) {
+    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap ta, tw, td;
+  if (int rc = make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, BLOCK_M)) return rc;
+  if (int rc = make_tmap_bf16(&tw, g.W, g.N, g.K, g.ldw, BLOCK_N)) return rc;
+  const int n_out = SWIGLU ? g.N / 2 : g.N;
+  if (int rc = make_tmap_bf16(&td, g.D, g.M, n_out, g.ldd, BLOCK_M)) return rc;
+  EpiParams ep;
+  ep.M = g.M; ep.N = g.N; ep.K = g.K;
+  ep.bias = g.bias; ep.row_scale = g.row_scale;
+  ep.resid = static_cast<const __nv_bfloat16*>(g.resid); ep.ldr = g.ldr; ep.act = g.act;
+  const int tiles = ceil_div(g.M, BLOCK_M) * ceil_div(g.N, BLOCK_N);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tw, td, ep);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// Pick the N tile that wastes the fewest tensor-core columns; prefer wide tiles on ties.
+int pick_block_n(int N, bool swiglu) {
+  const int cands_plain[4] = {256, 192, 128, 64};
+  const int cands_glu[2] = {256, 128};
+  const int* cands = swiglu ? cands_glu : cands_plain;
+  const int nc = swiglu ? 2 : 4;
+  int best = cands[0];
+  long long best_cost = -1;
+  for (int i = 0; i < nc; ++i) {
+    const int bn = cands[i];
+    const long long padded = static_cast<long long>(ceil_div(N, bn)) * bn;
+    // small penalty for narrow tiles (more epilogue/TMA overhead per flop)
+    const long long cost = padded * 16 + (256 - bn);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace
+
+int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
+  FVLA_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "empty GEMM");
+  FVLA_REQUIRE(g.K % 8 == 0 && g.lda % 8 == 0 && g.ldw % 8 == 0 && g.ldd % 8 == 0,
+               "bf16 GEMM needs K and leading dimensions in multiples of 8 elements");
+  if (g.swiglu) {
+    FVLA_REQUIRE(g.N % 16 == 0 && g.bias == nullptr && g.resid == nullptr && g.act == ACT_NONE,
+                 "SwiGLU epilogue takes interleaved gate/up columns and no bias/residual/activation");
+  }
+  if (g.resid != nullptr) FVLA_REQUIRE(g.ldr % 8 == 0, "residual pitch must be a multiple of 8");
+  const int bn = g.block_n > 0 ? g.block_n : pick_block_n(g.N, g.swiglu != 0);
+  if (g.swiglu) {
+    switch (bn) {
+      case 256: return launch_gemm<256, true>(g, stream);
+      case 128: return launch_gemm<128, true>(g, stream);
+      default: break;
+    }
+  } else {
+    switch (bn) {
+      case 256: return launch_gemm<256, false>(g, stream);
+      case 192: return launch_gemm<192, false>(g, stream);
+      case 128: return launch_gemm<128, false>(g, stream);
+      case 64: return launch_gemm<64, false>(g, stream);
+      default: break;
+    }
+  }
+  set_error("unsupported GEMM N tile " + std::to_string(bn));
+  return 2;
+}
+
+}  // namespace fvla

@@ -1,0 +1,109 @@
+// Host-callable launchers for every device kernel on the FastVLA forward path.
+// All tensors are NHWC / token-major. `dtype` selects the activation + GEMM-weight storage type
+// (DT_F32: fp32 parity mode, DT_BF16: throughput mode); accumulation is always fp32.
+// Every launcher is stream-ordered, allocates nothing and returns 0 on success (see last_error()).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace fvla {
+
+enum DType : int { DT_F32 = 0, DT_BF16 = 1, DT_U8 = 2 };
+inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : (dt == DT_BF16 ? 2 : 1); }
+
+// ---- GEMM: D[M,N] = epi(A[M,K] * W[N,K]^T) -----------------------------------------------
+struct GemmArgs {
+  const void* A = nullptr; int lda = 0;   // [M, K]
+  const void* W = nullptr; int ldw = 0;   // [N, K]  (torch Linear / 1x1-conv layout)
+  void* D = nullptr; int ldd = 0;         // [M, N]  ([M, N/2] with swiglu)
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;            // [N]
+  const float* row_scale = nullptr;       // [M], multiplies the accumulator (fused RMSNorm rstd)
+  const void* resid = nullptr; int ldr = 0;  // [M, N], added after the activation; may alias D
+  int act = 0;                            // Act enum
+  int swiglu = 0;                         // columns are interleaved (gate, up): out = silu(g) * u
+  int block_n = 0;                        // 0 = auto (bf16 path only)
+};
+int gemm_bf16(const GemmArgs& g, cudaStream_t stream);  // tcgen05 + TMA + TMEM
+int gemm_f32(const GemmArgs& g, cudaStream_t stream);   // FFMA, fp32 parity mode
+inline int gemm(int dtype, const GemmArgs& g, cudaStream_t s) {
+  return dtype == DT_BF16 ? gemm_bf16(g, s) : gemm_f32(g, s);
+}
+
+// ---- image ingest ----------------------------------------------------------------------------
+struct PreprocessArgs {
+  const void* src = nullptr; int src_dtype = DT_F32;  // DT_F32 / DT_U8 / DT_BF16
+  int src_nhwc = 0;         // 0: (B,C,h,w)   1: (B,h,w,C)
+  int B = 0, C = 3, h = 0, w = 0;
+  int S = 0;                // square output side
+  int letterbox = 1;        // aspect-preserving resize + left/top pad, else plain stretch
+  float pad_value = 0.f;
+  float scale = 1.f;        // value scale applied before the optional mean/std
+  int normalize = 0; float mean[3] = {0, 0, 0}; float inv_std[3] = {1, 1, 1};
+  void* dst = nullptr;      // (B,S,S,3) in `dtype`
+};
+int preprocess_images(int dtype, const PreprocessArgs& a, cudaStream_t stream);
+
+// ---- convolutions (NHWC) ---------------------------------------------------------------------
+// Dense 3x3 stride-2 pad-1 conv with 3 input channels (FastViTHD stem.0) + bias + GELU.
+// w_packed: [27][Cout] fp32 with row = (ky*3+kx)*3 + ci.
+int stem_conv3x3_s2(int dtype, const void* in, const float* w_packed, const float* bias, void* out,
+                    int B, int H, int W, int Cout, cudaStream_t stream);
+// Depthwise / grouped k x k conv, groups = Cin, Cout = mult*Cin (mult 1 or 2), pad k/2,
+// + bias (+ GELU).  w_packed: [k*k][Cout] fp32.
+int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, void* out, int B,
+           int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream);
+
+// ---- squeeze-excite tail of conv_exp ---------------------------------------------------------
+// x: [B, HW, C]; gate = sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2); out = gelu(x * gate)
+int se_gelu(int dtype, const void* x, void* out, int B, int HW, int C, int Cr, const float* w1,
+            const float* b1, const float* w2, const float* b2, float* scratch_mean,
+            float* scratch_gate, cudaStream_t stream);
+
+// ---- attention -------------------------------------------------------------------------------
+struct AttnArgs {
+  const void* q = nullptr; const void* k = nullptr; const void* v = nullptr;
+  int ld_qkv = 0;           // row pitch (elements) shared by q/k/v
+  void* o = nullptr; int ld_o = 0;
+  int B = 0, N = 0;         // N tokens per sample (rows of sample b start at b*N)
+  int heads_q = 0, heads_kv = 0, head_dim = 0;
+  float scale = 1.f;
+  int causal = 0;
+  const float* rope_cos = nullptr;  // [>=N][head_dim/2], null = no rotary embedding
+  const float* rope_sin = nullptr;
+};
+int attention(int dtype, const AttnArgs& a, cudaStream_t stream);       // bf16: mma.sync flash; f32: SIMT
+int attention_simt(int dtype, const AttnArgs& a, cudaStream_t stream);  // reference-grade SIMT for either dtype
+
+// ---- Qwen2 glue ------------------------------------------------------------------------------
+int rmsnorm(int dtype, const void* x, const float* weight, void* out, int rows, int H, float eps,
+            cudaStream_t stream);
+// plan[b*T+t]: >=0 vocab id, -1 zero row (padding), <=-2 image row (-2-idx) of sample b
+int embed_splice(int dtype, const void* table, const void* img_feats, int n_img, const int* plan,
+                 void* out, int B, int T, int H, cudaStream_t stream);
+// mode 0: last_token at pool_idx[b]; mode 1: mean over t < len[b]. Applies the final RMSNorm.
+int pool_norm(int dtype, const void* hidden, const float* norm_w, const int* pool_idx,
+              const int* lens, int mode, float* pooled, int B, int T, int H, float eps,
+              cudaStream_t stream);
+int swiglu_interleaved(int dtype, const void* gu, void* out, int rows, int I, cudaStream_t stream);
+
+// ---- FastVLA action head (fastvla/fastvlm_with_expert.py:23-38, 50-54) ------------------------
+struct HeadWeights {  // all fp32 except the four matrices, which are in `dtype`
+  const float* ln_s_w; const float* ln_s_b;        // state_projection.0
+  const void* w_state; const float* b_state;       // state_projection.1  [Hd, S]
+  const void* w_f0; const float* b_f0;             // fusion.0            [F, H+Hd]
+  const float* ln_f_w; const float* ln_f_b;        // fusion.1
+  const void* w_f4; const float* b_f4;             // fusion.4            [F, F]
+  const void* w_act; const float* b_act;           // action_head         [A, F]
+  int H, S, Hd, F, A;
+};
+// pooled [B,H] fp32, states [B,S] fp32 -> actions [B,A] fp32; optional taps (fp32) may be null
+int action_head(int dtype, const HeadWeights& w, const float* pooled, const float* states,
+                float* actions, float* tap_state_feat, float* tap_fused, int B,
+                cudaStream_t stream);
+
+// ---- small utilities -------------------------------------------------------------------------
+int convert(int src_dtype, const void* src, int dst_dtype, void* dst, long long n, cudaStream_t s);
+int rope_table(float* cos_t, float* sin_t, int T, int head_dim, float theta, cudaStream_t s);
+
+}  // namespace fvla

@@ -1,0 +1,215 @@
+// Small token-major kernels around the Qwen2 prefill: RMSNorm, token-embedding gather + LLaVA image
+// splice, final-norm + pooling, SwiGLU (unfused fallback form), dtype conversion, RoPE tables.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fvla {
+namespace {
+
+// Qwen2RMSNorm (transformers/models/qwen2/modeling_qwen2.py: Qwen2RMSNorm.forward):
+//   y = weight * (x * rsqrt(mean(x^2) + eps)), statistics in fp32.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rmsnorm_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ out, int H,
+               float eps) {
+  __shared__ float red[32];
+  const size_t row = blockIdx.x;
+  const T* xr = x + row * H;
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
+    Vec8<T> v; v.load(xr + i);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) ss = fmaf(v.v[c], v.v[c], ss);
+  }
+  ss = block_sum(ss, red);
+  const float rstd = rsqrtf(ss / static_cast<float>(H) + eps);
+  T* orow = out + row * H;
+  for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
+    Vec8<T> v; v.load(xr + i);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + i));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + i) + 1);
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v.v[c] = v.v[c] * rstd * wv[c];
+    v.store(orow + i);
+  }
+}
+
+// LLaVA prepare_inputs_labels_for_multimodal, materialised from a per-position plan.
+template <typename T>
+__global__ void embed_splice_kernel(const T* __restrict__ table, const T* __restrict__ img,
+                                    int n_img, const int* __restrict__ plan, T* __restrict__ out,
+                                    int T_len, int H) {
+  const size_t pos = blockIdx.x;  // b*T + t
+  const int b = static_cast<int>(pos / T_len);
+  const int code = plan[pos];
+  T* dst = out + pos * H;
+  const T* src = nullptr;
+  if (code >= 0) src = table + static_cast<size_t>(code) * H;
+  else if (code <= -2) src = img + (static_cast<size_t>(b) * n_img + (-2 - code)) * H;
+  for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
+    Vec8<T> v;
+    if (src) v.load(src + i);
+    else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v.v[c] = 0.f;
+    }
+    v.store(dst + i);
+  }
+}
+
+// Final RMSNorm fused with FastVLMBackbone._pool_hidden (fastvlm_adapter.py:337-359).
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_norm_kernel(const T* __restrict__ hidden, const float* __restrict__ w,
+                 const int* __restrict__ pool_idx, const int* __restrict__ lens, int mode,
+                 float* __restrict__ pooled, int T_len, int H, float eps) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float* dst = pooled + static_cast<size_t>(b) * H;
+  if (mode == 0) {
+    int idx = pool_idx[b];
+    idx = idx < 0 ? 0 : (idx >= T_len ? T_len - 1 : idx);
+    const T* xr = hidden + (static_cast<size_t>(b) * T_len + idx) * H;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { const float v = to_f32(xr[i]); ss = fmaf(v, v, ss); }
+    ss = block_sum(ss, red);
+    const float rstd = rsqrtf(ss / static_cast<float>(H) + eps);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) dst[i] = to_f32(xr[i]) * rstd * w[i];
+  } else {
+    const int n = lens[b];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) dst[i] = 0.f;
+    for (int t = 0; t < n; ++t) {
+      const T* xr = hidden + (static_cast<size_t>(b) * T_len + t) * H;
+      float ss = 0.f;
+      for (int i = threadIdx.x; i < H; i += blockDim.x) { const float v = to_f32(xr[i]); ss = fmaf(v, v, ss); }
+      ss = block_sum(ss, red);
+      const float rstd = rsqrtf(ss / static_cast<float>(H) + eps);
+      for (int i = threadIdx.x; i < H; i += blockDim.x) dst[i] += to_f32(xr[i]) * rstd * w[i];
+    }
+    const float denom = fmaxf(static_cast<float>(n), 1e-6f);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) dst[i] = dst[i] / denom;
+  }
+}
+
+template <typename T>
+__global__ void swiglu_kernel(const T* __restrict__ gu, T* __restrict__ out, long long total_vec,
+                              int I) {
+  // gu row: 2*I interleaved (g0,u0,g1,u1,...); each thread: 16 inputs -> 8 outputs
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  Vec8<T> a, b, r;
+  a.load(gu + idx * 16);
+  b.load(gu + idx * 16 + 8);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    r.v[c] = silu_precise(a.v[2 * c]) * a.v[2 * c + 1];
+    r.v[4 + c] = silu_precise(b.v[2 * c]) * b.v[2 * c + 1];
+  }
+  r.store(out + idx * 8);
+}
+
+template <typename TS, typename TD>
+__global__ void convert_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float v;
+    if constexpr (sizeof(TS) == 1) v = static_cast<float>(s[i]);
+    else v = to_f32(s[i]);
+    d[i] = from_f32<TD>(v);
+  }
+}
+
+// HF default rope: inv_freq[i] = theta^(-2i/d); cos/sin of pos*inv_freq in fp32.
+__global__ void rope_table_kernel(float* cos_t, float* sin_t, int T_len, int half, float theta) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T_len * half) return;
+  const int pos = idx / half, i = idx % half;
+  const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * i) / static_cast<float>(2 * half));
+  const float ang = static_cast<float>(pos) * inv_freq;
+  cos_t[idx] = cosf(ang);
+  sin_t[idx] = sinf(ang);
+}
+
+}  // namespace
+
+int rmsnorm(int dtype, const void* x, const float* weight, void* out, int rows, int H, float eps,
+            cudaStream_t stream) {
+  FVLA_REQUIRE(H % 8 == 0 && rows > 0, "rmsnorm: H%8");
+  if (dtype == DT_F32)
+    rmsnorm_kernel<float><<<rows, 128, 0, stream>>>(static_cast<const float*>(x), weight,
+                                                    static_cast<float*>(out), H, eps);
+  else
+    rmsnorm_kernel<__nv_bfloat16><<<rows, 128, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), weight, static_cast<__nv_bfloat16*>(out), H, eps);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int embed_splice(int dtype, const void* table, const void* img_feats, int n_img, const int* plan,
+                 void* out, int B, int T, int H, cudaStream_t stream) {
+  FVLA_REQUIRE(H % 8 == 0 && B > 0 && T > 0, "embed_splice: H%8");
+  if (dtype == DT_F32)
+    embed_splice_kernel<float><<<B * T, 128, 0, stream>>>(
+        static_cast<const float*>(table), static_cast<const float*>(img_feats), n_img, plan,
+        static_cast<float*>(out), T, H);
+  else
+    embed_splice_kernel<__nv_bfloat16><<<B * T, 128, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(img_feats),
+        n_img, plan, static_cast<__nv_bfloat16*>(out), T, H);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int pool_norm(int dtype, const void* hidden, const float* norm_w, const int* pool_idx,
+              const int* lens, int mode, float* pooled, int B, int T, int H, float eps,
+              cudaStream_t stream) {
+  if (dtype == DT_F32)
+    pool_norm_kernel<float><<<B, 256, 0, stream>>>(static_cast<const float*>(hidden), norm_w,
+                                                   pool_idx, lens, mode, pooled, T, H, eps);
+  else
+    pool_norm_kernel<__nv_bfloat16><<<B, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(hidden), norm_w, pool_idx, lens, mode, pooled, T, H, eps);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int swiglu_interleaved(int dtype, const void* gu, void* out, int rows, int I, cudaStream_t stream) {
+  FVLA_REQUIRE(I % 8 == 0, "swiglu: I%8");
+  const long long tv = static_cast<long long>(rows) * (I / 8);
+  const unsigned blocks = static_cast<unsigned>(ceil_div_ll(tv, 256));
+  if (dtype == DT_F32)
+    swiglu_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(gu),
+                                                     static_cast<float*>(out), tv, I);
+  else
+    swiglu_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(gu), static_cast<__nv_bfloat16*>(out), tv, I);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int convert(int sd, const void* src, int dd, void* dst, long long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const unsigned blocks = static_cast<unsigned>(ceil_div_ll(n, 256));
+#define FVLA_CVT(TS, TD)                                                                      \
+  convert_kernel<TS, TD><<<blocks, 256, 0, s>>>(static_cast<const TS*>(src), static_cast<TD*>(dst), n)
+  if (sd == DT_F32 && dd == DT_F32) FVLA_CVT(float, float);
+  else if (sd == DT_F32 && dd == DT_BF16) FVLA_CVT(float, __nv_bfloat16);
+  else if (sd == DT_BF16 && dd == DT_F32) FVLA_CVT(__nv_bfloat16, float);
+  else if (sd == DT_BF16 && dd == DT_BF16) FVLA_CVT(__nv_bfloat16, __nv_bfloat16);
+  else if (sd == DT_U8 && dd == DT_F32) FVLA_CVT(uint8_t, float);
+  else if (sd == DT_U8 && dd == DT_BF16) FVLA_CVT(uint8_t, __nv_bfloat16);
+  else { set_error("convert: unsupported dtype pair"); return 2; }
+#undef FVLA_CVT
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int rope_table(float* cos_t, float* sin_t, int T, int head_dim, float theta, cudaStream_t s) {
+  const int half = head_dim / 2;
+  rope_table_kernel<<<ceil_div(T * half, 256), 256, 0, s>>>(cos_t, sin_t, T, half, theta);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fvla
