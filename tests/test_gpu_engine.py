@@ -1,0 +1,162 @@
+"""End-to-end parity of the native engine (through the C ABI) against the CPU fp32 oracle on the tiny
+architecture, with per-stage tensors checked (north_star: actions within 1e-3 max-abs in fp32 and
+2e-2 relative in bf16)."""
+import pytest
+import torch
+
+from helpers import TINY_HEAD, make_engine, make_inputs, rel_err, tiny_weights
+
+pytestmark = pytest.mark.gpu
+
+FP32_STAGE_TOL = 2e-4   # relative to the stage's max |value|
+FP32_ACTION_TOL = 1e-3  # max-abs (north_star)
+BF16_STAGE_TOL = 6e-2
+BF16_ACTION_TOL = 2e-2  # relative (north_star)
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+
+
+def _run(dtype, image_mode, pool_mode="last_token", B=3, hw=(120, 160), T=9, vision_chunk=0, explicit_pool=False):
+    from oracle.fastvla_oracle import FastVLAOracle
+    from vla_fastvlm import _native as N
+
+    arch, sd, hsd = tiny_weights(0)
+    images, states, ids, mask = make_inputs(B, hw[0], hw[1], T, arch.text.vocab, TINY_HEAD["state_dim"], seed=3,
+                                            image_mode=image_mode)
+    oracle = FastVLAOracle(arch, sd, hsd, pool_mode=pool_mode)
+    taps = {}
+    pool_idx = None
+    if explicit_pool:  # last valid position of the MERGED sequence (what a prefix-mode user wants)
+        n_img = arch.vision.num_tokens if image_mode == "prefix" else 0
+        pool_idx = mask.sum(1) - 1 + (n_img - 1 if image_mode == "prefix" else 0)
+    ref = oracle.forward(images, states, ids, mask, pool_idx=pool_idx, taps=taps)
+
+    eng = make_engine(arch, sd, hsd, dtype, pool_mode=pool_mode, vision_chunk=vision_chunk)
+    dev = eng.device
+    v = arch.vision
+    S, H = v.image_size, arch.text.hidden
+    n_img = v.num_tokens
+    Tm = taps["embeds"].shape[1]
+    bufs = {}
+
+    def reg(stage, shape, dt=dtype):
+        bufs[stage] = torch.zeros(shape, device=dev, dtype=dt)
+        eng.set_tap(stage, bufs[stage])
+
+    has_img = image_mode == "prefix"
+    if has_img:
+        reg(N.TAP_PREPROCESS, (B, S, S, 4))
+        reg(N.TAP_STEM, (B, S // 4, S // 4, v.dims[0]))
+        side = S // 4
+        for i, d in enumerate(v.dims):
+            reg(N.TAP_VIS_STAGE0 + i, (B, side, side, d))
+            side //= 2
+        reg(N.TAP_IMAGE_FEATURES, (B, n_img, v.out_channels))
+        reg(N.TAP_PROJECTOR, (B, n_img, H))
+    reg(N.TAP_EMBEDS, (B, Tm, H))
+    for l in range(arch.text.layers):
+        reg(N.TAP_LAYER0 + l, (B, Tm, H))
+    reg(N.TAP_POOLED, (B, H), torch.float32)
+    reg(N.TAP_STATE_FEAT, (B, TINY_HEAD["hidden_dim"]), torch.float32)
+    reg(N.TAP_FUSED, (B, TINY_HEAD["fusion_dim"]), torch.float32)
+
+    out = eng.forward(images.to(dev), ids, mask.sum(1), states=states.to(dev), pool_idx=pool_idx)
+    torch.cuda.synchronize()
+    assert eng.merged_len == Tm
+    assert eng.last_launch_count > 0
+
+    stage_tol = FP32_STAGE_TOL if dtype == torch.float32 else BF16_STAGE_TOL
+    errs = {}
+    if has_img:
+        errs["preprocess"] = rel_err(bufs[N.TAP_PREPROCESS][..., :3], taps["preprocess"].permute(0, 2, 3, 1))
+        errs["stem"] = rel_err(bufs[N.TAP_STEM], taps["stem"].permute(0, 2, 3, 1))
+        for i in range(len(v.dims)):
+            errs[f"vis_stage{i}"] = rel_err(bufs[N.TAP_VIS_STAGE0 + i], taps[f"vis_stage{i}"].permute(0, 2, 3, 1))
+        errs["image_features"] = rel_err(bufs[N.TAP_IMAGE_FEATURES], taps["image_features"])
+        errs["projector"] = rel_err(bufs[N.TAP_PROJECTOR], taps["projector"])
+    errs["embeds"] = rel_err(bufs[N.TAP_EMBEDS], taps["embeds"])
+    valid = torch.zeros(B, Tm, dtype=torch.bool)
+    for b in range(B):
+        n = int(mask[b].sum()) + (n_img - 1 if has_img else 0)
+        valid[b, :n] = True
+    for l in range(arch.text.layers):
+        got = bufs[N.TAP_LAYER0 + l].float().cpu() * valid[..., None]
+        want = taps[f"layer{l}"] * valid[..., None]   # padded rows are never read by the reference
+        errs[f"layer{l}"] = rel_err(got, want)
+    errs["pooled"] = rel_err(bufs[N.TAP_POOLED], taps["pooled"])
+    errs["state_feat"] = rel_err(bufs[N.TAP_STATE_FEAT], taps["state_feat"])
+    errs["fused"] = rel_err(bufs[N.TAP_FUSED], taps["fused"])
+    bad = {k: v_ for k, v_ in errs.items() if not v_ <= stage_tol}
+    assert not bad, f"stages over tolerance {stage_tol}: {bad}\nall: {errs}"
+
+    out_c = out.float().cpu()
+    assert torch.isfinite(out_c).all()
+    if dtype == torch.float32:
+        assert (out_c - ref).abs().max().item() <= FP32_ACTION_TOL, errs
+    else:
+        assert rel_err(out_c, ref) <= BF16_ACTION_TOL, (errs, out_c, ref)
+    return errs
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("image_mode", ["prefix", "none"])
+def test_engine_matches_oracle(dtype, image_mode):
+    _need_gpu()
+    _run(dtype, image_mode)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_engine_explicit_pool_idx_and_chunking(dtype):
+    _need_gpu()
+    _run(dtype, "prefix", B=5, vision_chunk=2, explicit_pool=True)
+
+
+def test_engine_mean_pool_fp32():
+    _need_gpu()
+    _run(torch.float32, "none", pool_mode="mean_pool")
+
+
+def test_engine_square_image_no_pad_fp32():
+    _need_gpu()
+    _run(torch.float32, "prefix", hw=(256, 256), B=2)
+
+
+def test_engine_batch_invariance_bf16():
+    """Sample b of a batch equals the same sample run alone (rows are independent)."""
+    _need_gpu()
+    arch, sd, hsd = tiny_weights(0)
+    images, states, ids, mask = make_inputs(4, 96, 96, 7, arch.text.vocab, TINY_HEAD["state_dim"], seed=5)
+    eng = make_engine(arch, sd, hsd, torch.bfloat16)
+    dev = eng.device
+    full = eng.forward(images.to(dev), ids, mask.sum(1), states=states.to(dev)).clone()
+    for b in range(4):
+        n = int(mask[b].sum())
+        one = eng.forward(images[b:b + 1].to(dev), ids[b:b + 1, :n], mask[b:b + 1, :n].sum(1),
+                          states=states[b:b + 1].to(dev))
+        assert torch.allclose(one[0], full[b], atol=2e-2, rtol=2e-2), (b, one, full[b])
+
+
+def test_engine_errors():
+    _need_gpu()
+    from vla_fastvlm import _native as N
+
+    arch, sd, hsd = tiny_weights(0)
+    from vla_fastvlm.model.engine import NativeEngine
+
+    eng = NativeEngine(arch, dtype=torch.float32, **TINY_HEAD)
+    assert len(eng.missing_tensors()) > 100
+    with pytest.raises(N.NativeError, match="missing"):
+        eng.finalize()
+    eng2 = make_engine(arch, sd, hsd, torch.float32)
+    images, states, ids, mask = make_inputs(2, 64, 64, 5, arch.text.vocab, TINY_HEAD["state_dim"])
+    bad = ids.clone()
+    bad[0, 1] = arch.text.vocab + 7
+    with pytest.raises(N.NativeError, match="vocabulary"):
+        eng2.forward(images.cuda(), bad, mask.sum(1), states=states.cuda())
+    two = ids.clone()
+    two[0, 1] = -200
+    with pytest.raises(N.NativeError, match="placeholder"):
+        eng2.forward(images.cuda(), two, mask.sum(1), states=states.cuda())
