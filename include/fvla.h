@@ -138,6 +138,11 @@ enum {
 int fvla_set_tap(fvla_engine* e, int32_t stage, void* dst, int64_t capacity_bytes);
 int fvla_merged_len(fvla_engine* e);  /* T' of the last forward */
 
+/* Per-launch timing with CUDA events on the forward's stream (off by default).  The report is CSV:
+ * label,count,total_ms,flops,bytes — one line per distinct kernel/shape, device-synchronising. */
+int fvla_set_profile(fvla_engine* e, int32_t on);
+int fvla_profile_report(fvla_engine* e, char* buf, int64_t buf_len);
+
 /* ---- single-kernel entry points (used by the per-kernel parity tests and micro-benchmarks) ----
  * All pointers are device pointers; dtype selects fp32 / bf16 activations. */
 

@@ -116,6 +116,20 @@ int fvla_set_tap(fvla_engine* e, int32_t stage, void* dst, int64_t cap) {
   return e->impl.set_tap(stage, dst, cap);
 }
 int fvla_merged_len(fvla_engine* e) { return e ? e->impl.merged_len : 0; }
+int fvla_set_profile(fvla_engine* e, int32_t on) {
+  if (e == nullptr) { set_error("null engine"); return 2; }
+  e->impl.set_profile(on != 0);
+  return 0;
+}
+int fvla_profile_report(fvla_engine* e, char* buf, int64_t buf_len) {
+  if (e == nullptr || buf == nullptr || buf_len <= 0) { set_error("null argument"); return 2; }
+  std::string csv;
+  if (int rc = e->impl.profile_report(&csv)) return rc;
+  const size_t n = std::min<size_t>(csv.size(), static_cast<size_t>(buf_len - 1));
+  std::memcpy(buf, csv.data(), n);
+  buf[n] = '\0';
+  return 0;
+}
 
 // ---- single-kernel entry points ----
 int fvla_op_gemm(int32_t dtype, const void* A, int32_t lda, const void* W, int32_t ldw, void* D,

@@ -23,6 +23,55 @@ Engine::Engine(const fvla_config& c) : cfg(c) {}
 Engine::~Engine() {
   for (void* p : dev_allocs_) cudaFree(p);
   for (auto& kv : ws_.bufs) cudaFree(kv.second.first);
+  for (auto& p : prof_) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+  for (auto e : ev_pool_) cudaEventDestroy(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-launch profiling
+// ---------------------------------------------------------------------------------------------
+cudaEvent_t Engine::get_event() {
+  if (!ev_pool_.empty()) { cudaEvent_t e = ev_pool_.back(); ev_pool_.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void Engine::prof_begin(cudaStream_t s) {
+  if (!profile_) return;
+  prof_e0_ = get_event();
+  cudaEventRecord(prof_e0_, s);
+}
+void Engine::prof_end(const std::string& label, double fl, double by, cudaStream_t s) {
+  if (!profile_) return;
+  cudaEvent_t e1 = get_event();
+  cudaEventRecord(e1, s);
+  prof_.push_back({label, prof_e0_, e1, fl, by});
+  prof_e0_ = nullptr;
+}
+int Engine::profile_report(std::string* csv) {
+  FVLA_CUDA_CHECK(cudaDeviceSynchronize());
+  struct Agg { long long n = 0; double ms = 0, fl = 0, by = 0; };
+  std::map<std::string, Agg> agg;
+  std::vector<std::string> order;
+  for (auto& p : prof_) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.e0, p.e1);
+    if (agg.find(p.label) == agg.end()) order.push_back(p.label);
+    Agg& a = agg[p.label];
+    a.n += 1; a.ms += ms; a.fl += p.flops; a.by += p.bytes;
+    ev_pool_.push_back(p.e0);
+    ev_pool_.push_back(p.e1);
+  }
+  prof_.clear();
+  csv->clear();
+  *csv += "label,count,total_ms,flops,bytes\n";
+  char line[512];
+  for (auto& k : order) {
+    const Agg& a = agg[k];
+    snprintf(line, sizeof(line), "%s,%lld,%.6f,%.6e,%.6e\n", k.c_str(), a.n, a.ms, a.fl, a.by);
+    *csv += line;
+  }
+  return 0;
 }
 
 int Engine::n_img_tokens() const {
@@ -527,15 +576,38 @@ int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, con
   g.act = act;
   g.swiglu = swiglu ? 1 : 0;
   ++launches;
-  flops += 2.0 * M * static_cast<double>(w.N) * w.K;
-  return gemm(cfg.dtype, g, s);
+  const double fl = 2.0 * M * static_cast<double>(w.N) * w.K;
+  flops += fl;
+  prof_begin(s);
+  const int rc = gemm(cfg.dtype, g, s);
+  if (profile_) {
+    const double e = static_cast<double>(esz());
+    const double by = e * (static_cast<double>(M) * w.K + static_cast<double>(w.N) * w.K +
+                           static_cast<double>(M) * g.ldd + (resid ? static_cast<double>(M) * w.N : 0.0));
+    prof_end(std::string(prof_scope_) + "gemm M" + std::to_string(M) + " N" + std::to_string(w.N) + " K" +
+                 std::to_string(w.K) + (swiglu ? " swiglu" : "") + (resid ? " +res" : "") +
+                 (act == ACT_GELU ? " gelu" : ""),
+             fl, by, s);
+  }
+  return rc;
 }
 
 int Engine::run_dw(const DwW& w, const void* in, void* out, int B, int H, int W, cudaStream_t s) {
   ++launches;
   const int Ho = (H - 1) / w.stride + 1, Wo = (W - 1) / w.stride + 1;
-  flops += 2.0 * w.k * w.k * static_cast<double>(B) * Ho * Wo * w.cin * w.mult;
-  return dwconv(cfg.dtype, in, w.w, w.bias, out, B, H, W, w.cin, w.mult, w.k, w.stride, w.act, s);
+  const double fl = 2.0 * w.k * w.k * static_cast<double>(B) * Ho * Wo * w.cin * w.mult;
+  flops += fl;
+  prof_begin(s);
+  const int rc = dwconv(cfg.dtype, in, w.w, w.bias, out, B, H, W, w.cin, w.mult, w.k, w.stride, w.act, s);
+  if (profile_) {
+    const double e = static_cast<double>(esz());
+    const double by = e * (static_cast<double>(B) * H * W * w.cin + static_cast<double>(B) * Ho * Wo * w.cin * w.mult) +
+                      4.0 * (w.k * w.k + 1) * w.cin * w.mult;
+    prof_end("vis.dwconv k" + std::to_string(w.k) + " s" + std::to_string(w.stride) + " m" +
+                 std::to_string(w.mult) + " C" + std::to_string(w.cin) + " HW" + std::to_string(H),
+             fl, by, s);
+  }
+  return rc;
 }
 
 int Engine::reserve(int B, int n_tokens) {
@@ -629,7 +701,11 @@ int Engine::vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats
   for (int i = 0; i < 3; ++i) { pa.mean[i] = a.mean[i]; pa.inv_std[i] = a.inv_std[i]; }
   pa.dst = pre;
   ++launches;
+  prof_scope_ = "vis.";
+  prof_begin(s);
   if (int rc = preprocess_images(cfg.dtype, pa, s)) return rc;
+  prof_end("vis.preprocess", 0.0,
+           static_cast<double>(bc) * (img_elems * dtype_size(a.img_dtype) + static_cast<double>(S) * S * 4 * e), s);
   if (int rc = tap(FVLA_TAP_PREPROCESS, pre, static_cast<size_t>(bc) * S * S * 4 * e,
                    static_cast<size_t>(c0) * S * S * 4 * e, s)) return rc;
 
@@ -637,7 +713,10 @@ int Engine::vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats
   const int d0 = cfg.vis_dims[0];
   ++launches;
   flops += 2.0 * 27 * static_cast<double>(bc) * (S / 2) * (S / 2) * d0;
+  prof_begin(s);
   if (int rc = stem_conv3x3_s2(cfg.dtype, pre, stem0_w_, stem0_b_, Hb, bc, S, S, d0, s)) return rc;
+  prof_end("vis.stem_conv3x3", 2.0 * 27 * static_cast<double>(bc) * (S / 2) * (S / 2) * d0,
+           static_cast<double>(bc) * e * (static_cast<double>(S) * S * 4 + static_cast<double>(S / 2) * (S / 2) * d0), s);
   if (int rc = run_dw(stem1_, Hb, Z, bc, S / 2, S / 2, s)) return rc;
   int side = S / 4;
   if (int rc = run_gemm(stem2_, Z, X, bc * side * side, ACT_GELU, nullptr, false, s)) return rc;
@@ -673,7 +752,10 @@ int Engine::vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats
         at.causal = 0;
         ++launches;
         flops += 4.0 * bc * static_cast<double>(at.N) * at.N * d;
+        prof_begin(s);
         if (int rc = attention(cfg.dtype, at, s)) return rc;
+        prof_end("vis.attention N" + std::to_string(at.N) + " h" + std::to_string(at.heads_q),
+                 4.0 * bc * static_cast<double>(at.N) * at.N * d, 4.0 * M * static_cast<double>(d) * e, s);
         if (int rc = run_gemm(blk.proj, Z, X, M, ACT_NONE, X, false, s)) return rc;
         if (int rc = run_dw(blk.ffn_dw, X, Z, bc, side, side, s)) return rc;
         if (int rc = run_gemm(blk.fc1, Z, Hb, M, ACT_GELU, nullptr, false, s)) return rc;
@@ -693,9 +775,11 @@ int Engine::vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats
   const int ce = mm_hidden(), hw = side * side;
   launches += 3;
   char* dst = static_cast<char*>(feats) + static_cast<size_t>(c0) * hw * ce * e;
+  prof_begin(s);
   if (int rc = se_gelu(cfg.dtype, Z, dst, bc, hw, ce, cfg.vis_se_reduced, se_w1_, se_b1_, se_w2_,
                        se_b2_, static_cast<float*>(ws_.bufs["se_mean"].first),
                        static_cast<float*>(ws_.bufs["se_gate"].first), s)) return rc;
+  prof_end("vis.se_gelu", 0.0, 3.0 * bc * static_cast<double>(hw) * ce * e, s);
   return 0;
 }
 
@@ -761,6 +845,7 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
       if (int rc = vision_chunk(a, c0, bc, feats, s)) return rc;
     }
     if (int rc = tap(FVLA_TAP_IMAGE_FEATURES, feats, static_cast<size_t>(B) * nimg * mm_hidden() * e, 0, s)) return rc;
+    prof_scope_ = "proj.";
     if (int rc = run_gemm(proj0_, feats, proj_h, B * nimg, ACT_GELU, nullptr, false, s)) return rc;
     if (int rc = run_gemm(proj2_, proj_h, img_tok, B * nimg, ACT_NONE, nullptr, false, s)) return rc;
     if (int rc = tap(FVLA_TAP_PROJECTOR, img_tok, static_cast<size_t>(B) * nimg * H * e, 0, s)) return rc;
@@ -774,13 +859,18 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
   char* ACTB = static_cast<char*>(ws_.bufs["dec_act"].first);
   const int M = B * Tm;
   ++launches;
+  prof_scope_ = "llm.";
+  prof_begin(s);
   if (int rc = embed_splice(cfg.dtype, embed_, img_tok, nimg, d_plan, X, B, Tm, H, s)) return rc;
+  prof_end("llm.embed_splice", 0.0, 2.0 * M * static_cast<double>(H) * e, s);
   if (int rc = tap(FVLA_TAP_EMBEDS, X, static_cast<size_t>(M) * H * e, 0, s)) return rc;
   const int nq = cfg.n_q_heads, nkv = cfg.n_kv_heads, hd = cfg.head_dim;
   for (int l = 0; l < cfg.n_layers; ++l) {
     DecLayer& L = layers_[l];
     ++launches;
+    prof_begin(s);
     if (int rc = rmsnorm(cfg.dtype, X, L.ln1, Xn, M, H, cfg.rms_eps, s)) return rc;
+    prof_end("llm.rmsnorm", 0.0, 2.0 * M * static_cast<double>(H) * e, s);
     if (int rc = run_gemm(L.qkv, Xn, QKV, M, ACT_NONE, nullptr, false, s)) return rc;
     AttnArgs at;
     at.q = QKV; at.k = QKV + static_cast<size_t>(nq * hd) * e; at.v = QKV + static_cast<size_t>((nq + nkv) * hd) * e;
@@ -790,10 +880,15 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
     at.causal = 1; at.rope_cos = rope_cos_; at.rope_sin = rope_sin_;
     ++launches;
     flops += 2.0 * B * static_cast<double>(Tm) * Tm * nq * hd;  // causal: half of 4*T^2*d
+    prof_begin(s);
     if (int rc = attention(cfg.dtype, at, s)) return rc;
+    prof_end("llm.attention T" + std::to_string(Tm), 2.0 * B * static_cast<double>(Tm) * Tm * nq * hd,
+             static_cast<double>(M) * e * ((nq + 2 * nkv) * hd + nq * hd), s);
     if (int rc = run_gemm(L.o, AO, X, M, ACT_NONE, X, false, s)) return rc;
     ++launches;
+    prof_begin(s);
     if (int rc = rmsnorm(cfg.dtype, X, L.ln2, Xn, M, H, cfg.rms_eps, s)) return rc;
+    prof_end("llm.rmsnorm", 0.0, 2.0 * M * static_cast<double>(H) * e, s);
     if (int rc = run_gemm(L.gate_up, Xn, ACTB, M, ACT_NONE, nullptr, true, s)) return rc;
     if (int rc = run_gemm(L.down, ACTB, X, M, ACT_NONE, X, false, s)) return rc;
     if (int rc = tap(FVLA_TAP_LAYER0 + l, X, static_cast<size_t>(M) * H * e, 0, s)) return rc;
@@ -801,8 +896,10 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
   // ---- final norm + pooling ----
   float* pooled = static_cast<float*>(ws_.bufs["pooled"].first);
   ++launches;
+  prof_begin(s);
   if (int rc = pool_norm(cfg.dtype, X, final_norm_, d_pidx, d_lens, cfg.pool_mode, pooled, B, Tm, H,
                          cfg.rms_eps, s)) return rc;
+  prof_end("llm.pool_norm", 0.0, static_cast<double>(B) * H * (e + 4), s);
   if (int rc = tap(FVLA_TAP_POOLED, pooled, static_cast<size_t>(B) * H * 4, 0, s)) return rc;
   if (a.pooled != nullptr)
     FVLA_CUDA_CHECK(cudaMemcpyAsync(a.pooled, pooled, static_cast<size_t>(B) * H * 4,
@@ -817,7 +914,9 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
                         static_cast<double>(H + cfg.hidden_dim) * cfg.fusion_dim +
                         static_cast<double>(cfg.fusion_dim) * cfg.fusion_dim +
                         static_cast<double>(cfg.fusion_dim) * cfg.action_dim);
+    prof_begin(s);
     if (int rc = action_head(cfg.dtype, head_, pooled, a.states, a.actions, ts, tf, B, s)) return rc;
+    prof_end("head.action_head", 0.0, 0.0, s);
     if (int rc = tap(FVLA_TAP_STATE_FEAT, ts, static_cast<size_t>(B) * cfg.hidden_dim * 4, 0, s)) return rc;
     if (int rc = tap(FVLA_TAP_FUSED, tf, static_cast<size_t>(B) * cfg.fusion_dim * 4, 0, s)) return rc;
   }

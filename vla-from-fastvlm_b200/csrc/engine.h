@@ -59,6 +59,9 @@ class Engine {
   int reserve(int B, int n_tokens);
   int forward(const fvla_forward_args& a, cudaStream_t stream);
   int set_tap(int stage, void* dst, int64_t cap);
+  // per-launch CUDA-event profiling (off by default; adds two event records per kernel)
+  void set_profile(bool on) { profile_ = on; }
+  int profile_report(std::string* csv);  // syncs, aggregates by label, clears the samples
 
   fvla_config cfg;
   int64_t launches = 0;
@@ -112,6 +115,16 @@ class Engine {
 
   Workspace ws_;
   std::map<int, std::pair<void*, int64_t>> taps_;
+
+  struct ProfSample { std::string label; cudaEvent_t e0, e1; double flops, bytes; };
+  bool profile_ = false;
+  std::vector<ProfSample> prof_;
+  std::vector<cudaEvent_t> ev_pool_;
+  cudaEvent_t get_event();
+  void prof_begin(cudaStream_t s);
+  void prof_end(const std::string& label, double fl, double by, cudaStream_t s);
+  cudaEvent_t prof_e0_ = nullptr;
+  const char* prof_scope_ = "vis.";
 };
 
 }  // namespace fvla

@@ -108,6 +108,8 @@ _SIGNATURES = {
     "fvla_last_forward_flops": (C.c_double, [_VP]),
     "fvla_set_tap": (C.c_int, [_VP, _I32, _VP, _I64]),
     "fvla_merged_len": (C.c_int, [_VP]),
+    "fvla_set_profile": (C.c_int, [_VP, _I32]),
+    "fvla_profile_report": (C.c_int, [_VP, C.c_char_p, _I64]),
     "fvla_op_gemm": (C.c_int, [_I32, _VP, _I32, _VP, _I32, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP,
                                _I32, _I32, _I32, _I32, _VP]),
     "fvla_op_preprocess": (C.c_int, [_I32, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F32,

@@ -181,6 +181,22 @@ class NativeEngine:
             N.check(self.lib.fvla_forward(self._h, C.byref(a), N.stream_ptr()), "fvla_forward")
         return result
 
+    # ---- profiling ----------------------------------------------------------------------------
+    def set_profile(self, on: bool) -> None:
+        N.check(self.lib.fvla_set_profile(self._h, int(on)), "fvla_set_profile")
+
+    def profile_report(self) -> List[Dict[str, float]]:
+        """Per-kernel/shape totals since the last report: label, count, total_ms, flops, bytes."""
+        buf = C.create_string_buffer(1 << 20)
+        N.check(self.lib.fvla_profile_report(self._h, buf, len(buf)), "fvla_profile_report")
+        rows = []
+        for line in buf.value.decode().strip().split("\n")[1:]:
+            if not line:
+                continue
+            label, cnt, ms, fl, by = line.rsplit(",", 4)
+            rows.append(dict(label=label, count=int(cnt), total_ms=float(ms), flops=float(fl), bytes=float(by)))
+        return rows
+
     # ---- introspection ------------------------------------------------------------------------
     @property
     def last_launch_count(self) -> int:
