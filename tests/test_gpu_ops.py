@@ -149,7 +149,8 @@ def _pack_dw(w):  # [Cout,1,k,k] -> [k*k][Cout]
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("k,stride,mult,act", [(3, 1, 1, 0), (3, 2, 1, 1), (7, 1, 1, 0), (7, 2, 2, 1),
                                                (3, 1, 2, 0), (7, 2, 1, 0)])
-@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 16), (1, 37, 29, 24), (3, 64, 64, 96)])
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 16), (1, 37, 29, 24), (3, 64, 64, 96), (2, 8, 128, 32),
+                                     (1, 128, 128, 192)])
 def test_dwconv(native, dtype, k, stride, mult, act, B, H, W, C):
     dev = _dev()
     if stride == 2 and (H % 2 or W % 2):

@@ -307,21 +307,32 @@ int dwconv_dispatch(const void* in, const float* w, const float* bias, void* out
 // Squeeze-excite + GELU (conv_exp tail). mean over HW -> 2 tiny FCs -> sigmoid -> scale -> GELU
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void se_mean_kernel(const T* __restrict__ x, float* __restrict__ mean, int HW, int C) {
-  // grid: (C/8 / warps_per_block... , B); each thread owns 8 channels and strides over pixels
-  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+se_mean_kernel(const T* __restrict__ x, float* __restrict__ mean, int HW, int C) {
+  // grid (ceil(C/64), B); 256 threads = 8 channel vectors x 32 pixel lanes; pixels strided by 32
+  __shared__ float part[32][65];
+  const int cvl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cvl * 8;
   const int b = blockIdx.y;
-  if (cv * 8 >= C) return;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const T* p = x + static_cast<size_t>(b) * HW * C + cv * 8;
-  for (int i = 0; i < HW; ++i) {
-    Vec8<T> v; v.load(p + static_cast<size_t>(i) * C);
+  if (c0 < C) {
+    const T* p = x + static_cast<size_t>(b) * HW * C + c0;
+    for (int i = pl; i < HW; i += 32) {
+      Vec8<T> v; v.load(p + static_cast<size_t>(i) * C);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) s[c] += v.v[c];
+      for (int c = 0; c < 8; ++c) s[c] += v.v[c];
+    }
   }
-  const float inv = 1.f / static_cast<float>(HW);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) mean[static_cast<size_t>(b) * C + cv * 8 + c] = s[c] * inv;
+  for (int c = 0; c < 8; ++c) part[pl][cvl * 8 + c] = s[c];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) t += part[i][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < C) mean[static_cast<size_t>(b) * C + c] = t / static_cast<float>(HW);
+  }
 }
 
 // one block per sample: hidden = relu(W1 mean + b1) [Cr]; gate = sigmoid(W2 hidden + b2) [C]
@@ -370,8 +381,8 @@ template <typename T>
 int se_gelu_t(const void* x, void* out, int B, int HW, int C, int Cr, const float* w1,
               const float* b1, const float* w2, const float* b2, float* mean, float* gate,
               cudaStream_t s) {
-  dim3 g1(ceil_div(C / 8, 128), B);
-  se_mean_kernel<T><<<g1, 128, 0, s>>>(static_cast<const T*>(x), mean, HW, C);
+  dim3 g1(ceil_div(C, 64), B);
+  se_mean_kernel<T><<<g1, 256, 0, s>>>(static_cast<const T*>(x), mean, HW, C);
   se_fc_kernel<<<B, 256, (C + Cr) * sizeof(float), s>>>(mean, w1, b1, w2, b2, gate, C, Cr);
   const long long tv = static_cast<long long>(B) * HW * (C / 8);
   se_scale_gelu_kernel<T><<<static_cast<unsigned>(ceil_div_ll(tv, 256)), 256, 0, s>>>(
@@ -444,6 +455,8 @@ int stem_conv3x3_s2(int dtype, const void* in, const float* w_packed, const floa
 int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, void* out, int B,
            int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream) {
   FVLA_REQUIRE((Cin * mult) % 8 == 0, "dwconv: output channels must be a multiple of 8");
+  if (dwconv_tiled_supported(dtype, H, W, Cin, mult, ksize, stride))
+    return dwconv_tiled(in, w_packed, bias, out, B, H, W, Cin, ksize, act, stream);
   if (dtype == DT_F32)
     return dwconv_dispatch<float>(in, w_packed, bias, out, B, H, W, Cin, mult, ksize, stride, act, stream);
   return dwconv_dispatch<__nv_bfloat16>(in, w_packed, bias, out, B, H, W, Cin, mult, ksize, stride, act, stream);

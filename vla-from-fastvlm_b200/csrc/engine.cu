@@ -277,6 +277,13 @@ int Engine::pack_vision() {
     stem0_w_ = upload_f32(packed);
     stem0_b_ = upload_f32(b->data);
     FVLA_REQUIRE(stem0_w_ && stem0_b_, "cudaMalloc failed (stem)");
+    if (cfg.dtype == FVLA_BF16) {
+      // im2col form for the tensor cores: [d0][32] with column (ky*3+kx)*3+ci, columns 27..31 zero
+      std::vector<float> wg(32 * static_cast<size_t>(d0), 0.f);
+      for (int o = 0; o < d0; ++o)
+        for (int t = 0; t < 27; ++t) wg[static_cast<size_t>(o) * 32 + t] = packed[static_cast<size_t>(t) * d0 + o];
+      if (int rc = make_gemm(&stem0_gemm_, wg, d0, 32, &b->data)) return rc;
+    }
   }
   if (int rc = need(S(kVis, "patch_embed.1.reparam_conv.weight"), &w, {d0, 1, 3, 3})) return rc;
   if (int rc = need(S(kVis, "patch_embed.1.reparam_conv.bias"), &b, {d0})) return rc;
@@ -631,12 +638,14 @@ int Engine::reserve(int B, int n_tokens) {
   hid_max = std::max(hid_max, static_cast<size_t>(S / 2) * (S / 2) * cfg.vis_dims[0]);  // stem.0 output
   void* p;
   if (int rc = ensure("vis_pre", static_cast<size_t>(chunk) * S * S * 4 * e, &p)) return rc;
+  if (cfg.dtype == FVLA_BF16)
+    if (int rc = ensure("vis_col", static_cast<size_t>(chunk) * (S / 2) * (S / 2) * 32 * e, &p)) return rc;
   if (int rc = ensure("vis_x", chunk * act_max * e, &p)) return rc;
   if (int rc = ensure("vis_y", chunk * act_max * e, &p)) return rc;
   if (int rc = ensure("vis_z", chunk * act_max * e, &p)) return rc;
   if (int rc = ensure("vis_h", chunk * hid_max * e, &p)) return rc;
-  if (int rc = ensure("se_mean", static_cast<size_t>(chunk) * mm_hidden() * 4, &p)) return rc;
-  if (int rc = ensure("se_gate", static_cast<size_t>(chunk) * mm_hidden() * 4, &p)) return rc;
+  if (int rc = ensure("se_mean", static_cast<size_t>(B) * mm_hidden() * 4, &p)) return rc;
+  if (int rc = ensure("se_gate", static_cast<size_t>(B) * mm_hidden() * 4, &p)) return rc;
   const int nimg = n_img_tokens();
   const int H = cfg.hidden;
   if (int rc = ensure("feats", static_cast<size_t>(B) * nimg * mm_hidden() * e, &p)) return rc;
@@ -711,12 +720,25 @@ int Engine::vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats
 
   // ---- stem ----
   const int d0 = cfg.vis_dims[0];
-  ++launches;
-  flops += 2.0 * 27 * static_cast<double>(bc) * (S / 2) * (S / 2) * d0;
-  prof_begin(s);
-  if (int rc = stem_conv3x3_s2(cfg.dtype, pre, stem0_w_, stem0_b_, Hb, bc, S, S, d0, s)) return rc;
-  prof_end("vis.stem_conv3x3", 2.0 * 27 * static_cast<double>(bc) * (S / 2) * (S / 2) * d0,
-           static_cast<double>(bc) * e * (static_cast<double>(S) * S * 4 + static_cast<double>(S / 2) * (S / 2) * d0), s);
+  if (cfg.dtype == FVLA_BF16) {
+    // 27-tap patches -> [M, 32] bf16, then a K=32 tensor-core GEMM with bias + GELU in the epilogue
+    char* col = static_cast<char*>(ws_.bufs["vis_col"].first);
+    const int Ms = bc * (S / 2) * (S / 2);
+    ++launches;
+    prof_begin(s);
+    if (int rc = stem_im2col_bf16(pre, col, bc, S, S, s)) return rc;
+    prof_end("vis.stem_im2col", 0.0, static_cast<double>(bc) * e * (static_cast<double>(S) * S * 4 + static_cast<double>(Ms / bc) * 32), s);
+    const double before = flops;
+    if (int rc = run_gemm(stem0_gemm_, col, Hb, Ms, ACT_GELU, nullptr, false, s)) return rc;
+    flops = before + 2.0 * 27 * static_cast<double>(Ms) * d0;  // algorithmic taps, not the zero padding
+  } else {
+    ++launches;
+    flops += 2.0 * 27 * static_cast<double>(bc) * (S / 2) * (S / 2) * d0;
+    prof_begin(s);
+    if (int rc = stem_conv3x3_s2(cfg.dtype, pre, stem0_w_, stem0_b_, Hb, bc, S, S, d0, s)) return rc;
+    prof_end("vis.stem_conv3x3", 2.0 * 27 * static_cast<double>(bc) * (S / 2) * (S / 2) * d0,
+             static_cast<double>(bc) * e * (static_cast<double>(S) * S * 4 + static_cast<double>(S / 2) * (S / 2) * d0), s);
+  }
   if (int rc = run_dw(stem1_, Hb, Z, bc, S / 2, S / 2, s)) return rc;
   int side = S / 4;
   if (int rc = run_gemm(stem2_, Z, X, bc * side * side, ACT_GELU, nullptr, false, s)) return rc;
@@ -770,16 +792,10 @@ int Engine::vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats
       if (int rc = run_gemm(st.down_pw, Z, X, bc * side * side, ACT_GELU, nullptr, false, s)) return rc;
     }
   }
-  // ---- conv_exp + SE + GELU -> image features ----
-  if (int rc = run_dw(exp_dw_, X, Z, bc, side, side, s)) return rc;
+  // ---- conv_exp (grouped 3x3, x2 channels) -> pre-SE image features of this chunk ----
   const int ce = mm_hidden(), hw = side * side;
-  launches += 3;
   char* dst = static_cast<char*>(feats) + static_cast<size_t>(c0) * hw * ce * e;
-  prof_begin(s);
-  if (int rc = se_gelu(cfg.dtype, Z, dst, bc, hw, ce, cfg.vis_se_reduced, se_w1_, se_b1_, se_w2_,
-                       se_b2_, static_cast<float*>(ws_.bufs["se_mean"].first),
-                       static_cast<float*>(ws_.bufs["se_gate"].first), s)) return rc;
-  prof_end("vis.se_gelu", 0.0, 3.0 * bc * static_cast<double>(hw) * ce * e, s);
+  if (int rc = run_dw(exp_dw_, X, dst, bc, side, side, s)) return rc;
   return 0;
 }
 
@@ -843,6 +859,16 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
     for (int c0 = 0; c0 < B; c0 += chunk) {
       const int bc = std::min(chunk, B - c0);
       if (int rc = vision_chunk(a, c0, bc, feats, s)) return rc;
+    }
+    // squeeze-excite + GELU over the whole batch, in place (conv_exp tail)
+    {
+      const int ce = mm_hidden();
+      launches += 3;
+      prof_begin(s);
+      if (int rc = se_gelu(cfg.dtype, feats, feats, B, nimg, ce, cfg.vis_se_reduced, se_w1_, se_b1_, se_w2_,
+                           se_b2_, static_cast<float*>(ws_.bufs["se_mean"].first),
+                           static_cast<float*>(ws_.bufs["se_gate"].first), s)) return rc;
+      prof_end("vis.se_gelu", 0.0, 3.0 * B * static_cast<double>(nimg) * ce * e, s);
     }
     if (int rc = tap(FVLA_TAP_IMAGE_FEATURES, feats, static_cast<size_t>(B) * nimg * mm_hidden() * e, 0, s)) return rc;
     prof_scope_ = "proj.";

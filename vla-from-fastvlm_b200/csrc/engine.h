@@ -102,6 +102,7 @@ class Engine {
 
   // packed model
   float* stem0_w_ = nullptr; float* stem0_b_ = nullptr;
+  GemmW stem0_gemm_;  // bf16 mode: im2col form [d0][32]
   DwW stem1_; GemmW stem2_;
   std::vector<VisStage> stages_;
   DwW exp_dw_;

@@ -5,13 +5,20 @@
 // Activations are NHWC / token-major, so A is row-major [M, K]; torch keeps Linear and 1x1-conv
 // weights as [N, K] — both operands are K-major and go to the tensor core untouched.
 //
-// Structure (one persistent CTA per SM, 256 threads):
+// Structure (one persistent CTA per SM, 384 threads):
 //   warp 0     TMA producer: A/W tiles -> 128B-swizzled shared memory ring (mbarrier full/empty)
 //   warp 1     MMA issuer: one thread issues tcgen05.mma (128 x BLOCK_N x 16), accumulators in TMEM,
 //              two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warp 2     TMEM allocator
-//   warps 4-7  epilogue: tcgen05.ld -> row-scale / bias / activation / residual / SwiGLU -> bf16 ->
+//   warps 4-11 epilogue (two warps per TMEM lane quarter, each taking half of the columns):
+//              tcgen05.ld -> row-scale / bias / activation / residual / SwiGLU -> bf16 ->
 //              swizzled staging tile -> TMA store (bounds clipped by the tensor map)
+//
+// The small-K GEMMs of the vision tower (K = 96..384) are epilogue-bound, not MMA-bound: each output
+// element gets only 2K tensor-core flops, so the activation has to cost ~10 issue slots.  The bf16
+// path therefore evaluates GELU as x*(0.5+0.5*tanh(P(x))) with P fitted to the erf form (formula error
+// 2.5e-5 abs, one MUFU.TANH, relative error <= 2.5e-4 — 1/8 of a bf16 half-ulp); the fp32 parity mode
+// (gemm_f32.cu) keeps erff.
 //
 // Edges need no special code: TMA zero-fills out-of-bounds loads (M, N and K tails) and clips stores.
 #include "common.cuh"
@@ -27,8 +34,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
-constexpr int EPI_THREADS = 128;
+constexpr int GEMM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
 constexpr int STAGING_BYTES = BLOCK_M * 64 * 2;  // 128 rows x 64 bf16 output columns
 
 template <int BLOCK_N> struct GemmCfg {
@@ -53,6 +60,23 @@ struct EpiParams {
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf-GELU to 2.5e-5 (+ MUFU.TANH's 2^-11 relative error): see the header comment.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float x2 = x * x;
+  const float p = x * fmaf(x2, fmaf(x2, -3.51516789e-04f, 3.70056460e-02f), 7.97507884e-01f);
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(p), h);
+}
+// x * sigmoid(x) = 0.5x * (1 + tanh(0.5x)): one MUFU
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
 }
 
 template <int BLOCK_N, bool SWIGLU>
@@ -165,8 +189,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
-    const int epi_tid = threadIdx.x - 128;  // == tile row == TMEM lane
-    const int ew = warp_idx - 4;            // TMEM lane quarter this warp may read
+    const int ew = warp_idx & 3;            // TMEM lane quarter this warp may read (warp_idx % 4)
+    const int chalf = (warp_idx - 4) >> 2;  // which half of each sub-tile's columns this warp owns
+    const int row = ew * 32 + lane;         // tile row == TMEM lane
+    const bool store_leader = (warp_idx == 4 && lane == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     int sbuf = 0;
@@ -174,7 +200,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * BLOCK_M;
       const int n0 = (tile % num_n) * BLOCK_N;
-      const int m = m0 + epi_tid;
+      const int m = m0 + row;
       const bool row_ok = m < p.M;
       float rs = 1.0f;
       if (p.row_scale != nullptr && row_ok) rs = __ldg(p.row_scale + m);
@@ -190,12 +216,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int out_col0 = (SWIGLU ? (n0 / 2) : n0) + sub * 64;  // first output column
         if (out_col0 >= n_out_total) break;                     // whole sub-tile out of range
         // the TMA store issued from this staging buffer two sub-tiles ago must have read it
-        if (epi_tid == 0) ptx::tma_store_wait_read<1>();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const uint32_t sbase = smem_stage0 + sbuf * STAGING_BYTES + epi_tid * 128;
+        if (store_leader) ptx::tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const uint32_t sbase = smem_stage0 + sbuf * STAGING_BYTES + row * 128;
 
+        constexpr int Q_PER_WARP = ACC_PER_SUB / 64;  // 32-column chunks per warp per sub-tile
 #pragma unroll
-        for (int q = 0; q < ACC_PER_SUB / 32; ++q) {
+        for (int qq = 0; qq < Q_PER_WARP; ++qq) {
+          const int q = chalf * Q_PER_WARP + qq;
           uint32_t r[32];
           ptx::tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(acc_col0 + q * 32), r);
           ptx::tmem_ld_wait();
@@ -208,14 +236,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             uint32_t o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float a0 = silu_precise(v[4 * j]) * v[4 * j + 1];
-              const float a1 = silu_precise(v[4 * j + 2]) * v[4 * j + 3];
+              const float a0 = silu_fast(v[4 * j]) * v[4 * j + 1];
+              const float a1 = silu_fast(v[4 * j + 2]) * v[4 * j + 3];
               o[j] = pack_bf16(a0, a1);
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               const int chunk = 2 * q + c;
-              const uint32_t dst = sbase + ((chunk ^ (epi_tid & 7)) << 4);
+              const uint32_t dst = sbase + ((chunk ^ (row & 7)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[4 * c]),
                            "r"(o[4 * c + 1]), "r"(o[4 * c + 2]), "r"(o[4 * c + 3])
                            : "memory");
@@ -237,10 +265,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             if (p.act == ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
             } else if (p.act == ACT_SILU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = silu_precise(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
             }
             if (p.resid != nullptr && row_ok) {
               const __nv_bfloat16* rp = p.resid + static_cast<size_t>(m) * p.ldr + nb;
@@ -264,7 +292,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const int chunk = 4 * q + c;
-              const uint32_t dst = sbase + ((chunk ^ (epi_tid & 7)) << 4);
+              const uint32_t dst = sbase + ((chunk ^ (row & 7)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
                            "r"(pack_bf16(v[8 * c], v[8 * c + 1])),
                            "r"(pack_bf16(v[8 * c + 2], v[8 * c + 3])),
@@ -275,8 +303,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
         ptx::fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (epi_tid == 0) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (store_leader) {
           ptx::tma_store_2d(&tmap_d, out_col0, m0, smem_stage0 + sbuf * STAGING_BYTES);
           ptx::tma_store_commit();
         }
@@ -287,7 +315,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       ptx::mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (epi_tid == 0) ptx::tma_store_wait<0>();
+    if (store_leader) ptx::tma_store_wait<0>();
   }
 
   ptx::tc_fence_before();

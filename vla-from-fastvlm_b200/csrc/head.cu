@@ -13,26 +13,44 @@ namespace {
 
 template <typename T> __device__ __forceinline__ float ld_w(const T* p) { return to_f32(*p); }
 
-// y[r][n] = sum_k x[r][k] * W[n][k]  for one output column n, all R rows; K % 8 == 0.
-template <typename T, int R>
-__device__ __forceinline__ void warp_dot_rows(const T* __restrict__ wrow, const float* x, int ldx,
-                                              int K, int lane, float (&acc)[R]) {
+// y[r][n0+j] = sum_k x[r][k] * W[n0+j][k] for NC consecutive output columns and all R rows; K % 8 == 0.
+// NC independent weight streams per warp keep several 128-bit loads in flight (the head is
+// latency-bound: 6 MB of weights read once by a handful of CTAs).
+template <typename T, int R, int NC>
+__device__ __forceinline__ void warp_dot_rows(const T* __restrict__ wbase, int ldw, int n_valid,
+                                              const float* x, int ldx, int K, int lane,
+                                              float (&acc)[NC][R]) {
 #pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  for (int j = 0; j < NC; ++j)
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
   for (int k = lane * 8; k < K; k += 32 * 8) {
-    Vec8<T> w; w.load(wrow + k);
+    Vec8<T> w[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      if (j < n_valid) w[j].load(wbase + static_cast<size_t>(j) * ldw + k);
+      else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w[j].v[c] = 0.f;
+      }
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float4 x0 = *reinterpret_cast<const float4*>(x + r * ldx + k);
       const float4 x1 = *reinterpret_cast<const float4*>(x + r * ldx + k + 4);
-      float a = acc[r];
-      a = fmaf(w.v[0], x0.x, a); a = fmaf(w.v[1], x0.y, a); a = fmaf(w.v[2], x0.z, a); a = fmaf(w.v[3], x0.w, a);
-      a = fmaf(w.v[4], x1.x, a); a = fmaf(w.v[5], x1.y, a); a = fmaf(w.v[6], x1.z, a); a = fmaf(w.v[7], x1.w, a);
-      acc[r] = a;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        float a = acc[j][r];
+        a = fmaf(w[j].v[0], x0.x, a); a = fmaf(w[j].v[1], x0.y, a); a = fmaf(w[j].v[2], x0.z, a); a = fmaf(w[j].v[3], x0.w, a);
+        a = fmaf(w[j].v[4], x1.x, a); a = fmaf(w[j].v[5], x1.y, a); a = fmaf(w[j].v[6], x1.z, a); a = fmaf(w[j].v[7], x1.w, a);
+        acc[j][r] = a;
+      }
     }
   }
 #pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+  for (int j = 0; j < NC; ++j)
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[j][r] = warp_sum(acc[j][r]);
 }
 
 template <typename T, int R>
@@ -49,6 +67,7 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
   const int r0 = blockIdx.x * R;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwarps = blockDim.x >> 5;
+  constexpr int NC = 4;
 
   // ---- LayerNorm(state) (eps 1e-5, biased variance) ----
   if (warp < R) {
@@ -100,12 +119,17 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
   // ---- fusion.0: Linear(KC -> F) ----
   {
     const T* wf = static_cast<const T*>(w.w_f0);
-    for (int n = warp; n < F; n += nwarps) {
-      float acc[R];
-      warp_dot_rows<T, R>(wf + static_cast<size_t>(n) * KC, cat, KC, KC, lane, acc);
+    for (int n0 = warp * NC; n0 < F; n0 += nwarps * NC) {
+      float acc[NC][R];
+      const int nv = F - n0 < NC ? F - n0 : NC;
+      warp_dot_rows<T, R, NC>(wf + static_cast<size_t>(n0) * KC, KC, nv, cat, KC, KC, lane, acc);
       if (lane == 0) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) x1[r * F + n] = acc[r] + w.b_f0[n];
+        for (int j = 0; j < NC; ++j)
+          if (j < nv) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) x1[r * F + n0 + j] = acc[j][r] + w.b_f0[n0 + j];
+          }
       }
     }
   }
@@ -125,16 +149,21 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
   // ---- fusion.4: Linear(F -> F) + SiLU ----
   {
     const T* wf = static_cast<const T*>(w.w_f4);
-    for (int n = warp; n < F; n += nwarps) {
-      float acc[R];
-      warp_dot_rows<T, R>(wf + static_cast<size_t>(n) * F, x1, F, F, lane, acc);
+    for (int n0 = warp * NC; n0 < F; n0 += nwarps * NC) {
+      float acc[NC][R];
+      const int nv = F - n0 < NC ? F - n0 : NC;
+      warp_dot_rows<T, R, NC>(wf + static_cast<size_t>(n0) * F, F, nv, x1, F, F, lane, acc);
       if (lane == 0) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float y = silu_precise(acc[r] + w.b_f4[n]);
-          x2[r * F + n] = y;
-          if (tap_fused != nullptr && r0 + r < B) tap_fused[static_cast<size_t>(r0 + r) * F + n] = y;
-        }
+        for (int j = 0; j < NC; ++j)
+          if (j < nv) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const float y = silu_precise(acc[j][r] + w.b_f4[n0 + j]);
+              x2[r * F + n0 + j] = y;
+              if (tap_fused != nullptr && r0 + r < B) tap_fused[static_cast<size_t>(r0 + r) * F + n0 + j] = y;
+            }
+          }
       }
     }
   }
@@ -143,12 +172,12 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
   {
     const T* wa = static_cast<const T*>(w.w_act);
     for (int n = warp; n < A; n += nwarps) {
-      float acc[R];
-      warp_dot_rows<T, R>(wa + static_cast<size_t>(n) * F, x2, F, F, lane, acc);
+      float acc[1][R];
+      warp_dot_rows<T, R, 1>(wa + static_cast<size_t>(n) * F, F, 1, x2, F, F, lane, acc);
       if (lane == 0) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
-          if (r0 + r < B) actions[static_cast<size_t>(r0 + r) * A + n] = acc[r] + w.b_act[n];
+          if (r0 + r < B) actions[static_cast<size_t>(r0 + r) * A + n] = acc[0][r] + w.b_act[n];
       }
     }
   }
@@ -157,7 +186,7 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
 template <typename T>
 int launch_head(const HeadWeights& w, const float* pooled, const float* states, float* actions,
                 float* tap_state, float* tap_fused, int B, cudaStream_t stream) {
-  constexpr int R = 4;
+  constexpr int R = 2;
   auto kfn = action_head_kernel<T, R>;
   const size_t smem = sizeof(float) * (static_cast<size_t>(R) * (w.H + w.Hd + 2 * w.F + w.S));
   FVLA_REQUIRE(smem <= 220 * 1024, "action head: hidden sizes too large for one CTA");

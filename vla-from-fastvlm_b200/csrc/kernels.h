@@ -49,10 +49,17 @@ int preprocess_images(int dtype, const PreprocessArgs& a, cudaStream_t stream);
 // w_packed: [27][Cout] fp32 with row = (ky*3+kx)*3 + ci.
 int stem_conv3x3_s2(int dtype, const void* in, const float* w_packed, const float* bias, void* out,
                     int B, int H, int W, int Cout, cudaStream_t stream);
+// bf16 tensor-core route for the same conv: gather 27-tap patches into [B*(H/2)*(W/2), 32] (cols 27..31 zero)
+int stem_im2col_bf16(const void* in, void* col, int B, int H, int W, cudaStream_t stream);
 // Depthwise / grouped k x k conv, groups = Cin, Cout = mult*Cin (mult 1 or 2), pad k/2,
 // + bias (+ GELU).  w_packed: [k*k][Cout] fp32.
 int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, void* out, int B,
            int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream);
+
+// smem-tiled bf16 fast path (stride 1, mult 1, k in {3,7}, W%64==0, H%8==0, C%32==0); dwconv() uses it
+bool dwconv_tiled_supported(int dtype, int H, int W, int C, int mult, int k, int stride);
+int dwconv_tiled(const void* in, const float* w_packed, const float* bias, void* out, int B, int H,
+                 int W, int C, int k, int act, cudaStream_t stream);
 
 // ---- squeeze-excite tail of conv_exp ---------------------------------------------------------
 // x: [B, HW, C]; gate = sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2); out = gelu(x * gate)
