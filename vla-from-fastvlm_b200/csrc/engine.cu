@@ -86,7 +86,6 @@ int Engine::mm_hidden() const { return cfg.vis_dims[cfg.vis_num_stages - 1] * 2;
 // ---------------------------------------------------------------------------------------------
 int Engine::load_tensor(const char* name, const void* data, int dtype, int ndim,
                         const int64_t* shape) {
-  FVLA_REQUIRE(!finalized_, "load_tensor after finalize");
   FVLA_REQUIRE(name != nullptr && data != nullptr && ndim >= 0 && ndim <= 8, "bad tensor");
   HostTensor t;
   t.shape.assign(shape, shape + ndim);
@@ -104,6 +103,7 @@ int Engine::load_tensor(const char* name, const void* data, int dtype, int ndim,
     set_error("load_tensor: dtype must be fp32 or bf16");
     return 2;
   }
+  if (finalized_) return update_head_tensor(name, t);
   host_[name] = std::move(t);
   return 0;
 }
@@ -179,9 +179,11 @@ std::vector<std::string> Engine::required_names() const {
     r.push_back(b + ".mlp.down_proj.weight");
   }
   r.push_back(S(kLlm, "norm.weight"));
-  wb("state_projection.0"); wb("state_projection.1");
-  wb("fusion.0"); wb("fusion.1"); wb("fusion.4");
-  wb("action_head");
+  if (cfg.state_dim > 0) {  // state_dim 0 = backbone-only engine (FastVLMBackbone used on its own)
+    wb("state_projection.0"); wb("state_projection.1");
+    wb("fusion.0"); wb("fusion.1"); wb("fusion.4");
+    wb("action_head");
+  }
   return r;
 }
 
@@ -476,30 +478,50 @@ int Engine::pack_decoder() {
 
 int Engine::pack_head() {
   const int H = cfg.hidden, Sd = cfg.state_dim, Hd = cfg.hidden_dim, F = cfg.fusion_dim, A = cfg.action_dim;
-  const HostTensor *a, *b;
   head_.H = H; head_.S = Sd; head_.Hd = Hd; head_.F = F; head_.A = A;
-  if (int rc = need("state_projection.0.weight", &a, {Sd})) return rc;
-  if (int rc = need("state_projection.0.bias", &b, {Sd})) return rc;
-  head_.ln_s_w = upload_f32(a->data); head_.ln_s_b = upload_f32(b->data);
-  if (int rc = need("state_projection.1.weight", &a, {Hd, Sd})) return rc;
-  if (int rc = need("state_projection.1.bias", &b, {Hd})) return rc;
-  head_.w_state = upload_act(a->data); head_.b_state = upload_f32(b->data);
-  if (int rc = need("fusion.0.weight", &a, {F, H + Hd})) return rc;
-  if (int rc = need("fusion.0.bias", &b, {F})) return rc;
-  head_.w_f0 = upload_act(a->data); head_.b_f0 = upload_f32(b->data);
-  if (int rc = need("fusion.1.weight", &a, {F})) return rc;
-  if (int rc = need("fusion.1.bias", &b, {F})) return rc;
-  head_.ln_f_w = upload_f32(a->data); head_.ln_f_b = upload_f32(b->data);
-  if (int rc = need("fusion.4.weight", &a, {F, F})) return rc;
-  if (int rc = need("fusion.4.bias", &b, {F})) return rc;
-  head_.w_f4 = upload_act(a->data); head_.b_f4 = upload_f32(b->data);
-  if (int rc = need("action_head.weight", &a, {A, F})) return rc;
-  if (int rc = need("action_head.bias", &b, {A})) return rc;
-  head_.w_act = upload_act(a->data); head_.b_act = upload_f32(b->data);
-  FVLA_REQUIRE(head_.ln_s_w && head_.ln_s_b && head_.w_state && head_.b_state && head_.w_f0 &&
-                   head_.b_f0 && head_.ln_f_w && head_.ln_f_b && head_.w_f4 && head_.b_f4 &&
-                   head_.w_act && head_.b_act,
-               "cudaMalloc failed (head)");
+  // name -> (destination slot, element count, stored in engine dtype?)
+  struct Slot { const char* name; const void** dst; int64_t n; bool act; };
+  const Slot slots[] = {
+      {"state_projection.0.weight", reinterpret_cast<const void**>(&head_.ln_s_w), Sd, false},
+      {"state_projection.0.bias", reinterpret_cast<const void**>(&head_.ln_s_b), Sd, false},
+      {"state_projection.1.weight", &head_.w_state, static_cast<int64_t>(Hd) * Sd, true},
+      {"state_projection.1.bias", reinterpret_cast<const void**>(&head_.b_state), Hd, false},
+      {"fusion.0.weight", &head_.w_f0, static_cast<int64_t>(F) * (H + Hd), true},
+      {"fusion.0.bias", reinterpret_cast<const void**>(&head_.b_f0), F, false},
+      {"fusion.1.weight", reinterpret_cast<const void**>(&head_.ln_f_w), F, false},
+      {"fusion.1.bias", reinterpret_cast<const void**>(&head_.ln_f_b), F, false},
+      {"fusion.4.weight", &head_.w_f4, static_cast<int64_t>(F) * F, true},
+      {"fusion.4.bias", reinterpret_cast<const void**>(&head_.b_f4), F, false},
+      {"action_head.weight", &head_.w_act, static_cast<int64_t>(A) * F, true},
+      {"action_head.bias", reinterpret_cast<const void**>(&head_.b_act), A, false},
+  };
+  for (const Slot& sl : slots) {
+    const HostTensor* t;
+    if (int rc = need(sl.name, &t, {sl.n})) return rc;
+    void* p = sl.act ? upload_act(t->data) : static_cast<void*>(upload_f32(t->data));
+    FVLA_REQUIRE(p != nullptr, "cudaMalloc failed (head)");
+    *sl.dst = p;
+    head_slots_[sl.name] = {p, sl.n, sl.act};
+  }
+  return 0;
+}
+
+// Trainable head parameters may change between forwards (FastVLAPolicy.forward trains only the
+// head): overwrite the packed copy in place.
+int Engine::update_head_tensor(const std::string& name, const HostTensor& t) {
+  auto it = head_slots_.find(name);
+  if (it == head_slots_.end()) {
+    set_error("load_tensor after finalize is only allowed for action-head tensors, got: " + name);
+    return 2;
+  }
+  FVLA_REQUIRE(t.numel() == it->second.n, "head tensor size changed");
+  if (it->second.act && cfg.dtype == FVLA_BF16) {
+    std::vector<__nv_bfloat16> h(t.data.size());
+    for (size_t i = 0; i < h.size(); ++i) h[i] = __float2bfloat16_rn(t.data[i]);
+    FVLA_CUDA_CHECK(cudaMemcpy(it->second.ptr, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  } else {
+    FVLA_CUDA_CHECK(cudaMemcpy(it->second.ptr, t.data.data(), t.data.size() * 4, cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
@@ -519,7 +541,8 @@ int Engine::finalize() {
   }
   if (int rc = pack_vision()) return rc;
   if (int rc = pack_decoder()) return rc;
-  if (int rc = pack_head()) return rc;
+  if (cfg.state_dim > 0)
+    if (int rc = pack_head()) return rc;
   host_.clear();
   finalized_ = true;
   FVLA_CUDA_CHECK(cudaDeviceSynchronize());
@@ -933,6 +956,7 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
   // ---- action head ----
   if (a.states != nullptr) {
     FVLA_REQUIRE(a.actions != nullptr, "forward: actions buffer required with states");
+    FVLA_REQUIRE(cfg.state_dim > 0, "forward: this engine was built without an action head");
     float* ts = static_cast<float*>(ws_.bufs["tap_state"].first);
     float* tf = static_cast<float*>(ws_.bufs["tap_fused"].first);
     ++launches;

@@ -83,6 +83,9 @@ class Engine {
   int pack_vision();
   int pack_decoder();
   int pack_head();
+  int update_head_tensor(const std::string& name, const HostTensor& t);
+  struct HeadSlot { void* ptr; int64_t n; bool act; };
+  std::map<std::string, HeadSlot> head_slots_;
 
   int ensure(const std::string& name, size_t bytes, void** out);
   int tap(int stage, const void* src, size_t bytes, size_t dst_offset_bytes, cudaStream_t s);

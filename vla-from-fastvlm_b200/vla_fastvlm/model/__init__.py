@@ -1,0 +1,3 @@
+from .fastvlm_adapter import FastVLMBackbone, FastVLMBackboneConfig
+
+__all__ = ["FastVLMBackbone", "FastVLMBackboneConfig"]

@@ -13,11 +13,12 @@ Keys are those of `LlavaQwen2ForCausalLM.state_dict()`; hea
 from __future__ import annotations
 
 import math
-from typing import Dict
+from typing import TYPE_CHECKING, Dict
 
 import torch
 
-from .arch import BackboneArch
+if TYPE_CHECKING:  # keep this module loadable by file path (tests/golden/make_golden.py)
+    from .arch import BackboneArch
 
 VIS_PREFIX = "model.vision_tower.vision_tower.model."
 PROJ_PREFIX = "model.mm_projector."
@@ -44,7 +45,7 @@ class _Init:
         sd[prefix + ".running_var"] = self.uniform(c, lo=0.6, hi=1.4)
 
 
-def synthetic_backbone_state_dict(arch: BackboneArch, seed: int = 0) -> Dict[str, torch.Tensor]:
+def synthetic_backbone_state_dict(arch: "BackboneArch", seed: int = 0) -> Dict[str, torch.Tensor]:
     r = _Init(seed)
     sd: Dict[str, torch.Tensor] = {}
     v, t = arch.vision, arch.text
