@@ -302,3 +302,18 @@ def test_se_gelu(native, dtype):
     gate = torch.sigmoid(F.relu(xf.mean(1) @ w1.t() + b1) @ w2.t() + b2)
     ref = F.gelu(xf * gate[:, None, :])
     _close(out, ref, BF16_TOL if dtype == torch.bfloat16 else F32_TOL, "se_gelu")
+
+
+def test_gemm_bf16_gelu_large_magnitudes(native):
+    """The MUFU-based GELU must stay exact-in-bf16 far outside the fitted range (|x| up to ~300)."""
+    dev = _dev()
+    g = torch.Generator().manual_seed(77)
+    M, N, K = 512, 256, 64
+    a = (torch.randn(M, K, generator=g) * 12).to(dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.4).to(dev).bfloat16()
+    out = native.op_gemm(a, w, act=1)
+    ref = F.gelu(a.float() @ w.float().t())
+    assert ref.abs().max() > 100
+    _close(out, ref, BF16_TOL, "gelu large")
+    pos = ref > 20
+    assert torch.allclose(out.float()[pos], ref[pos], rtol=1e-2)

@@ -68,8 +68,10 @@ __device__ __forceinline__ float tanh_approx(float x) {
 }
 // erf-GELU to 2.5e-5 (+ MUFU.TANH's 2^-11 relative error): see the header comment.
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float x2 = x * x;
-  const float p = x * fmaf(x2, fmaf(x2, -3.51516789e-04f, 3.70056460e-02f), 7.97507884e-01f);
+  // the fitted polynomial is only monotone on |x| < ~9: clamp its argument (P(8) = 13.8, tanh == 1)
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
+  const float x2 = xc * xc;
+  const float p = xc * fmaf(x2, fmaf(x2, -3.51516789e-04f, 3.70056460e-02f), 7.97507884e-01f);
   const float h = 0.5f * x;
   return fmaf(h, tanh_approx(p), h);
 }
