@@ -31,7 +31,8 @@ extern "C" {
 #define FVLA_IMAGE_TOKEN_INDEX (-200) /* LLaVA placeholder id spliced by the backbone [EXT] */
 
 enum { FVLA_F32 = 0, FVLA_BF16 = 1, FVLA_U8 = 2 };
-enum { FVLA_ACT_NONE = 0, FVLA_ACT_GELU = 1, FVLA_ACT_SILU = 2, FVLA_ACT_RELU = 3 };
+/* FVLA_ACT_GELU_HALF: operand is x/2 (weights + bias pre-halved by the caller), result gelu(x) */
+enum { FVLA_ACT_NONE = 0, FVLA_ACT_GELU = 1, FVLA_ACT_SILU = 2, FVLA_ACT_RELU = 3, FVLA_ACT_GELU_HALF = 4 };
 enum { FVLA_POOL_LAST_TOKEN = 0, FVLA_POOL_MEAN = 1 }; /* fastvlm_adapter.py:337-359 */
 
 #define FVLA_MAX_VIS_STAGES 8

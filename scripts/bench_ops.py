@@ -66,3 +66,23 @@ if __name__ == "__main__":
         bench_dwconv(a.batch)
     if "gemm" in a.what:
         bench_gemm(a.batch)
+
+
+def bench_gemm_epilogues():
+    print("# epilogue cost at fixed shape (bf16)")
+    for (M, Nn, K) in [(524288, 768, 192), (131072, 1536, 384), (131072, 384, 1536)]:
+        a = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(Nn, K, device="cuda") / K ** 0.5).bfloat16()
+        bias = torch.randn(Nn, device="cuda")
+        out = torch.empty(M, Nn, device="cuda", dtype=torch.bfloat16)
+        r = torch.randn(M, Nn, device="cuda").bfloat16()
+        for name, kw in [("plain", {}), ("bias", dict(bias=bias)), ("bias+gelu", dict(bias=bias, act=1)),
+                         ("bias+silu", dict(bias=bias, act=2)), ("bias+res", dict(bias=bias, resid=r))]:
+            for bn in (0, 128, 256):
+                ms = timeit(lambda: N.op_gemm(a, w, out=out, block_n=bn, **kw))
+                print(f"M{M} N{Nn} K{K} {name:10s} bn={bn:3d}: {ms:7.3f} ms {2.0 * M * Nn * K / ms / 1e9:7.1f} TFLOP/s "
+                      f"{2.0 * (M * K + M * Nn) / ms / 1e6:7.1f} GB/s")
+
+
+if __name__ == "__main__" and "epi" in sys.argv:
+    bench_gemm_epilogues()

@@ -1,0 +1,18 @@
+"""Launch one GEMM shape a few times (ncu target)."""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "vla-from-fastvlm_b200"))
+import torch  # noqa: E402
+
+from vla_fastvlm import _native as N  # noqa: E402
+
+M, Nn, K, act = [int(v) for v in sys.argv[1:5]]
+a = torch.randn(M, K, device="cuda").bfloat16()
+w = (torch.randn(Nn, K, device="cuda") / K ** 0.5).bfloat16()
+bias = torch.randn(Nn, device="cuda")
+out = torch.empty(M, Nn, device="cuda", dtype=torch.bfloat16)
+for _ in range(4):
+    N.op_gemm(a, w, bias=bias, act=act, out=out)
+torch.cuda.synchronize()
+print("ok", float(out.float().abs().mean()))

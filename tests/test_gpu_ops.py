@@ -317,3 +317,17 @@ def test_gemm_bf16_gelu_large_magnitudes(native):
     _close(out, ref, BF16_TOL, "gelu large")
     pos = ref > 20
     assert torch.allclose(out.float()[pos], ref[pos], rtol=1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_gelu_half_operand(native, dtype):
+    """ACT_GELU_HALF (4): weights/bias pre-scaled by 1/2, epilogue returns gelu(2h)."""
+    dev = _dev()
+    g = torch.Generator().manual_seed(31)
+    M, N, K = 700, 384, 96
+    a = torch.randn(M, K, generator=g).to(dev).to(dtype)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K) * 2).to(dev).to(dtype)
+    bias = torch.randn(N, generator=g).to(dev)
+    out = native.op_gemm(a, (w * 0.5).contiguous(), bias=bias * 0.5, act=4)
+    ref = F.gelu(a.float() @ w.float().t() + bias)
+    _close(out, ref, BF16_TOL if dtype == torch.bfloat16 else F32_TOL, "gelu half")

@@ -357,6 +357,7 @@ int attention(int dtype, const AttnArgs& a, cudaStream_t stream) {
   if (a.head_dim == 128 && a.causal && rope) return launch_flash<128, true, true>(a, stream);
   if (a.head_dim == 64 && !a.causal && !rope) return launch_flash<64, false, false>(a, stream);
   if (a.head_dim == 64 && a.causal && !rope) return launch_flash<64, true, false>(a, stream);
+  if (a.head_dim == 128 && a.causal && !rope) return launch_flash<128, true, false>(a, stream);
   set_error("attention: no flash instantiation for head_dim=" + std::to_string(a.head_dim) +
             " causal=" + std::to_string(a.causal) + " rope=" + std::to_string(rope ? 1 : 0));
   return 2;

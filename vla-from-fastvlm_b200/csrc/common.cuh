@@ -30,7 +30,8 @@ const char* last_error();
     }                                                                                      \
   } while (0)
 
-enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_RELU = 3 };
+// ACT_GELU_HALF: the operand is x/2 (weights and bias pre-scaled by 1/2 at pack time), result gelu(x)
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_RELU = 3, ACT_GELU_HALF = 4 };
 
 // ---- scalar conversions -------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }
@@ -59,6 +60,7 @@ __device__ __forceinline__ float apply_act_rt(float x, int act) {
     case ACT_GELU: return gelu_erf(x);
     case ACT_SILU: return silu_precise(x);
     case ACT_RELU: return fmaxf(x, 0.0f);
+    case ACT_GELU_HALF: return gelu_erf(2.0f * x);
     default: return x;
   }
 }

@@ -296,8 +296,8 @@ int dwconv_dispatch(const void* in, const float* w, const float* bias, void* out
   if (k == 3 && stride == 2 && mult == 1) return launch_dwconv<T, 3, 2, 1, 2>(in, w, bias, out, B, H, W, Cin, act, s);
   if (k == 3 && stride == 1 && mult == 2) return launch_dwconv<T, 3, 1, 2, 4>(in, w, bias, out, B, H, W, Cin, act, s);
   if (k == 7 && stride == 1 && mult == 1) return launch_dwconv<T, 7, 1, 1, 4>(in, w, bias, out, B, H, W, Cin, act, s);
-  if (k == 7 && stride == 2 && mult == 2) return launch_dwconv<T, 7, 2, 2, 2>(in, w, bias, out, B, H, W, Cin, act, s);
-  if (k == 7 && stride == 2 && mult == 1) return launch_dwconv<T, 7, 2, 1, 2>(in, w, bias, out, B, H, W, Cin, act, s);
+  if (k == 7 && stride == 2 && mult == 2) return launch_dwconv<T, 7, 2, 2, 4>(in, w, bias, out, B, H, W, Cin, act, s);
+  if (k == 7 && stride == 2 && mult == 1) return launch_dwconv<T, 7, 2, 1, 4>(in, w, bias, out, B, H, W, Cin, act, s);
   set_error("dwconv: unsupported (k, stride, mult) = (" + std::to_string(k) + ", " +
             std::to_string(stride) + ", " + std::to_string(mult) + ")");
   return 2;

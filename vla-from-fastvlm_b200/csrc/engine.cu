@@ -220,9 +220,23 @@ void* Engine::upload_act(const std::vector<float>& v) {
   return p;
 }
 
-int Engine::make_gemm(GemmW* g, const std::vector<float>& w, int N, int K,
-                      const std::vector<float>* bias) {
-  FVLA_REQUIRE(static_cast<int64_t>(w.size()) == static_cast<int64_t>(N) * K, "gemm weight size");
+int Engine::make_gemm(GemmW* g, const std::vector<float>& w_in, int N, int K,
+                      const std::vector<float>* bias_in, bool gelu_half) {
+  FVLA_REQUIRE(static_cast<int64_t>(w_in.size()) == static_cast<int64_t>(N) * K, "gemm weight size");
+  // GELU GEMMs produce x/2 (scaling by a power of two is exact) so the epilogue saves two multiplies
+  std::vector<float> w_scaled, b_scaled;
+  const std::vector<float>* bias = bias_in;
+  if (gelu_half) {
+    w_scaled.resize(w_in.size());
+    for (size_t i = 0; i < w_in.size(); ++i) w_scaled[i] = 0.5f * w_in[i];
+    if (bias_in != nullptr) {
+      b_scaled.resize(bias_in->size());
+      for (size_t i = 0; i < bias_in->size(); ++i) b_scaled[i] = 0.5f * (*bias_in)[i];
+      bias = &b_scaled;
+    }
+  }
+  const std::vector<float>& w = gelu_half ? w_scaled : w_in;
+  g->half_in = gelu_half;
   g->N = N; g->K = K;
   g->w = upload_act(w);
   FVLA_REQUIRE(g->w != nullptr, "cudaMalloc failed for a GEMM weight");
@@ -284,7 +298,7 @@ int Engine::pack_vision() {
       std::vector<float> wg(32 * static_cast<size_t>(d0), 0.f);
       for (int o = 0; o < d0; ++o)
         for (int t = 0; t < 27; ++t) wg[static_cast<size_t>(o) * 32 + t] = packed[static_cast<size_t>(t) * d0 + o];
-      if (int rc = make_gemm(&stem0_gemm_, wg, d0, 32, &b->data)) return rc;
+      if (int rc = make_gemm(&stem0_gemm_, wg, d0, 32, &b->data, true)) return rc;
     }
   }
   if (int rc = need(S(kVis, "patch_embed.1.reparam_conv.weight"), &w, {d0, 1, 3, 3})) return rc;
@@ -292,7 +306,7 @@ int Engine::pack_vision() {
   if (int rc = make_dw(&stem1_, w->data, b->data, d0, 1, 3, 2, ACT_GELU)) return rc;
   if (int rc = need(S(kVis, "patch_embed.2.reparam_conv.weight"), &w, {d0, d0, 1, 1})) return rc;
   if (int rc = need(S(kVis, "patch_embed.2.reparam_conv.bias"), &b, {d0})) return rc;
-  if (int rc = make_gemm(&stem2_, w->data, d0, d0, &b->data)) return rc;
+  if (int rc = make_gemm(&stem2_, w->data, d0, d0, &b->data, true)) return rc;
 
   // ---- stages ----
   auto pack_ffn = [&](const std::string& base, int d, const HostTensor* ls, VisBlock* blk) -> int {
@@ -316,7 +330,7 @@ int Engine::pack_vision() {
       dwb[c] = static_cast<float>(t[c]);
     }
     if (int rc = make_dw(&blk->ffn_dw, dw, dwb, d, 1, 7, 1, ACT_NONE)) return rc;
-    if (int rc = make_gemm(&blk->fc1, f1w->data, hd, d, &f1b->data)) return rc;
+    if (int rc = make_gemm(&blk->fc1, f1w->data, hd, d, &f1b->data, true)) return rc;
     // x + ls * (W h + b)  ==  x + (ls.W) h + ls.b
     std::vector<float> w2(f2w->data.size()), b2(static_cast<size_t>(d));
     for (int n = 0; n < d; ++n) {
@@ -401,7 +415,7 @@ int Engine::pack_vision() {
       if (int rc = need(p + ".proj.1.reparam_conv.bias", &pb, {d2})) return rc;
       st.has_down = true;
       if (int rc = make_dw(&st.down_dw, lw->data, lb->data, d, 2, 7, 2, ACT_GELU)) return rc;
-      if (int rc = make_gemm(&st.down_pw, pw->data, d2, d2, &pb->data)) return rc;
+      if (int rc = make_gemm(&st.down_pw, pw->data, d2, d2, &pb->data, true)) return rc;
     }
   }
   // ---- conv_exp ----
@@ -420,7 +434,7 @@ int Engine::pack_vision() {
   const int H = cfg.hidden;
   if (int rc = need(S(kProj, "0.weight"), &w, {H, ce})) return rc;
   if (int rc = need(S(kProj, "0.bias"), &b, {H})) return rc;
-  if (int rc = make_gemm(&proj0_, w->data, H, ce, &b->data)) return rc;
+  if (int rc = make_gemm(&proj0_, w->data, H, ce, &b->data, true)) return rc;
   if (int rc = need(S(kProj, "2.weight"), &w, {H, H})) return rc;
   if (int rc = need(S(kProj, "2.bias"), &b, {H})) return rc;
   return make_gemm(&proj2_, w->data, H, H, &b->data);
@@ -603,7 +617,7 @@ int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, con
   g.M = M; g.N = w.N; g.K = w.K;
   g.bias = w.bias;
   g.resid = resid; g.ldr = w.N;
-  g.act = act;
+  g.act = (act == ACT_GELU && w.half_in) ? static_cast<int>(ACT_GELU_HALF) : act;
   g.swiglu = swiglu ? 1 : 0;
   ++launches;
   const double fl = 2.0 * M * static_cast<double>(w.N) * w.K;
@@ -645,7 +659,7 @@ int Engine::reserve(int B, int n_tokens) {
   FVLA_REQUIRE(B > 0 && n_tokens > 0, "reserve: empty");
   const size_t e = esz();
   const int S = cfg.image_size;
-  int chunk = cfg.vision_chunk > 0 ? cfg.vision_chunk : 8;
+  int chunk = cfg.vision_chunk > 0 ? cfg.vision_chunk : 32;
   chunk = std::min(chunk, B);
   // per-image maxima over the tower
   size_t act_max = 0, hid_max = 0;
@@ -877,7 +891,7 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
   void* img_tok = ws_.bufs["img_tok"].first;
   if (any_image || !cfg.skip_unused_vision) {
     FVLA_REQUIRE(a.images != nullptr, "forward: images required");
-    int chunk = cfg.vision_chunk > 0 ? cfg.vision_chunk : 8;
+    int chunk = cfg.vision_chunk > 0 ? cfg.vision_chunk : 32;
     chunk = std::min(chunk, B);
     for (int c0 = 0; c0 < B; c0 += chunk) {
       const int bc = std::min(chunk, B - c0);
@@ -926,7 +940,11 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
     at.ld_qkv = (nq + 2 * nkv) * hd; at.o = AO; at.ld_o = nq * hd;
     at.B = B; at.N = Tm; at.heads_q = nq; at.heads_kv = nkv; at.head_dim = hd;
     at.scale = 1.0f / std::sqrt(static_cast<float>(hd));
-    at.causal = 1; at.rope_cos = rope_cos_; at.rope_sin = rope_sin_;
+    at.causal = 1;  // q and k were rotated in place just above
+    ++launches;
+    prof_begin(s);
+    if (int rc = rope_inplace(cfg.dtype, QKV, at.ld_qkv, B, Tm, nq + nkv, hd, rope_cos_, rope_sin_, s)) return rc;
+    prof_end("llm.rope", 0.0, 2.0 * M * static_cast<double>((nq + nkv) * hd) * e, s);
     ++launches;
     flops += 2.0 * B * static_cast<double>(Tm) * Tm * nq * hd;  // causal: half of 4*T^2*d
     prof_begin(s);

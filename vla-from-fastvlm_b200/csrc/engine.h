@@ -20,6 +20,7 @@ struct GemmW {  // packed nn.Linear / 1x1 conv
   void* w = nullptr;          // [N, K] in engine dtype
   const float* bias = nullptr;  // [N] fp32 or null
   int N = 0, K = 0;
+  bool half_in = false;       // weights+bias pre-scaled by 1/2: the GELU epilogue takes x/2 (ACT_GELU_HALF)
 };
 struct DwW {  // packed depthwise / grouped conv
   float* w = nullptr;     // [k*k][Cout] fp32
@@ -77,7 +78,8 @@ class Engine {
 
   float* upload_f32(const std::vector<float>& v);
   void* upload_act(const std::vector<float>& v);  // engine dtype
-  int make_gemm(GemmW* g, const std::vector<float>& w, int N, int K, const std::vector<float>* bias);
+  int make_gemm(GemmW* g, const std::vector<float>& w, int N, int K, const std::vector<float>* bias,
+                bool gelu_half = false);
   int make_dw(DwW* d, const std::vector<float>& w_oihw, const std::vector<float>& bias, int cin,
               int mult, int k, int stride, int act);
   int pack_vision();

@@ -5,20 +5,15 @@
 // Activations are NHWC / token-major, so A is row-major [M, K]; torch keeps Linear and 1x1-conv
 // weights as [N, K] — both operands are K-major and go to the tensor core untouched.
 //
-// Structure (one persistent CTA per SM, 384 threads):
+// Structure (one persistent CTA per SM, 640 threads):
 //   warp 0     TMA producer: A/W tiles -> 128B-swizzled shared memory ring (mbarrier full/empty)
 //   warp 1     MMA issuer: one thread issues tcgen05.mma (128 x BLOCK_N x 16), accumulators in TMEM,
 //              two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warp 2     TMEM allocator
-//   warps 4-11 epilogue (two warps per TMEM lane quarter, each taking half of the columns):
+//   warps 4-19 epilogue (four warps per TMEM lane quarter, each taking a quarter of the columns):
 //              tcgen05.ld -> row-scale / bias / activation / residual / SwiGLU -> bf16 ->
 //              swizzled staging tile -> TMA store (bounds clipped by the tensor map)
 //
-// The small-K GEMMs of the vision tower (K = 96..384) are epilogue-bound, not MMA-bound: each output
-// element gets only 2K tensor-core flops, so the activation has to cost ~10 issue slots.  The bf16
-// path therefore evaluates GELU as x*(0.5+0.5*tanh(P(x))) with P fitted to the erf form (formula error
-// 2.5e-5 abs, one MUFU.TANH, relative error <= 2.5e-4 — 1/8 of a bf16 half-ulp); the fp32 parity mode
-// (gemm_f32.cu) keeps erff.
 //
 // Edges need no special code: TMA zero-fills out-of-bounds loads (M, N and K tails) and clips stores.
 #include "common.cuh"
@@ -34,9 +29,11 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 384;
-constexpr int EPI_THREADS = 256;
-constexpr int STAGING_BYTES = BLOCK_M * 64 * 2;  // 128 rows x 64 bf16 output columns
+constexpr int EPI_WPQ = 4;                        // epilogue warps per TMEM lane quarter
+constexpr int EPI_THREADS = 4 * EPI_WPQ * 32;     // 512
+constexpr int GEMM_THREADS = 128 + EPI_THREADS;   // 640
+constexpr int STAGING_BYTES = BLOCK_M * 64 * 2;  // 128 rows x 64 bf16 output columns (per buffer)
+constexpr int SLAB_BYTES = 32 * 64 * 2;          // one lane quarter's 32-row slab
 
 template <int BLOCK_N> struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -61,21 +58,44 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// ---- epilogue activations -----------------------------------------------------------------------
+// The XU (MUFU) pipe is the scarce resource of the small-K GEMM epilogues: ncu shows it 100 % busy at
+// ~4 tanh/clk/SM (profiles/r01_gemm_gelu_k192_ncu.txt), i.e. 8192 cycles for a 128x256 tile whose MMAs
+// take 1536-3072.  ex2+rcp is no better (two MUFU ops).  GELU is therefore evaluated two ways and the
+// elements of a thread are split between them so that the XU and FMA pipes finish together:
+//   3 of 8 elements:  h + h*tanh(h*Q(h^2))          1 MUFU + 7 FP32 slots   (|err| <= 2.5e-5 + 2^-11 rel)
+//   5 of 8 elements:  h + h*th*R(th^2), th=clamp(h) 0 MUFU + 11 FP32 slots  (|err| <= 1.9e-4)
+// both in terms of h = x/2 (GELU GEMMs are packed with weights/bias pre-halved, exact in bf16), both
+// approximations of the erf form nn.GELU() computes.  The fp32 parity mode keeps erff.
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// erf-GELU to 2.5e-5 (+ MUFU.TANH's 2^-11 relative error): see the header comment.
-__device__ __forceinline__ float gelu_fast(float x) {
-  // the fitted polynomial is only monotone on |x| < ~9: clamp its argument (P(8) = 13.8, tanh == 1)
-  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
-  const float x2 = xc * xc;
-  const float p = xc * fmaf(x2, fmaf(x2, -3.51516789e-04f, 3.70056460e-02f), 7.97507884e-01f);
-  const float h = 0.5f * x;
-  return fmaf(h, tanh_approx(p), h);
+// Phi(x) = (1 + tanh(P(x)))/2 with P fitted to atanh(erf(x/sqrt2)); h^2 clamped where tanh has saturated
+__device__ __forceinline__ float gelu_half_mufu(float h) {
+  const float u = fminf(h * h, 16.0f);
+  const float q = fmaf(u, fmaf(u, -1.124853725e-02f, 2.96045168e-01f), 1.594015768f);
+  return fmaf(h, tanh_approx(h * q), h);
 }
-// x * sigmoid(x) = 0.5x * (1 + tanh(0.5x)): one MUFU
+// erf(x/sqrt2) ~= x*R(x^2) on |x| <= 4 (odd minimax polynomial, 7 coefficients), +-1 outside
+__device__ __forceinline__ float gelu_half_poly(float h) {
+  const float th = fminf(fmaxf(h, -2.0f), 2.0f);
+  const float s = th * th;
+  float r = fmaf(s, 3.732471752e-04f, -6.547819094e-03f);
+  r = fmaf(s, r, 4.910614436e-02f);
+  r = fmaf(s, r, -2.083871470e-01f);
+  r = fmaf(s, r, 5.614317921e-01f);
+  r = fmaf(s, r, -1.033169161e+00f);
+  r = fmaf(s, r, 1.591533285e+00f);
+  return fmaf(h, th * r, h);
+}
+template <int N>
+__device__ __forceinline__ void gelu_half_hybrid(float (&v)[N]) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = ((j & 7) % 3 == 0) ? gelu_half_mufu(v[j]) : gelu_half_poly(v[j]);
+}
+// x * sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU (SwiGLU has one per TWO accumulators)
 __device__ __forceinline__ float silu_fast(float x) {
   const float h = 0.5f * x;
   return fmaf(h, tanh_approx(h), h);
@@ -191,14 +211,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
+    // Each TMEM lane quarter (32 tile rows) is served by EPI_WPQ warps that share a private
+    // 32-row x 64-column staging slab (double buffered) and their own TMA stores; a quarter only
+    // synchronises with itself (128-thread named barriers), never CTA-wide.  Four warps per
+    // scheduler give the MUFU/LDTM/LDG latencies something to hide behind.
     const int ew = warp_idx & 3;            // TMEM lane quarter this warp may read (warp_idx % 4)
-    const int chalf = (warp_idx - 4) >> 2;  // which half of each sub-tile's columns this warp owns
+    const int cq = (warp_idx - 4) >> 2;     // which slice of each sub-tile's columns this warp owns
     const int row = ew * 32 + lane;         // tile row == TMEM lane
-    const bool store_leader = (warp_idx == 4 && lane == 0);
+    const int tq = cq * 32 + lane;          // thread index within the quarter's group
+    constexpr int QT = EPI_WPQ * 32;        // threads per quarter group
+    const bool q_leader = (cq == 0 && lane == 0);
+    const uint32_t slab0 = smem_stage0 + static_cast<uint32_t>(ew) * (2 * SLAB_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
     int sbuf = 0;
     const int n_out_total = SWIGLU ? p.N / 2 : p.N;
+    constexpr int CPW = ACC_PER_SUB / EPI_WPQ;  // accumulator columns per warp per sub-tile (16 or 32)
+    constexpr int NCH = CPW / 16;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * BLOCK_M;
       const int n0 = (tile % num_n) * BLOCK_N;
@@ -217,84 +246,110 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int acc_col0 = sub * ACC_PER_SUB;                 // first accumulator column
         const int out_col0 = (SWIGLU ? (n0 / 2) : n0) + sub * 64;  // first output column
         if (out_col0 >= n_out_total) break;                     // whole sub-tile out of range
-        // the TMA store issued from this staging buffer two sub-tiles ago must have read it
-        if (store_leader) ptx::tma_store_wait_read<1>();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const uint32_t sbase = smem_stage0 + sbuf * STAGING_BYTES + row * 128;
+        const uint32_t slab = slab0 + static_cast<uint32_t>(sbuf) * SLAB_BYTES;
 
-        constexpr int Q_PER_WARP = ACC_PER_SUB / 64;  // 32-column chunks per warp per sub-tile
+        // residual sub-tile (32 rows x 128 B): coalesced 16-byte loads, issued before anything else
+        constexpr int RPT = 256 / QT;  // 16-byte residual chunks per thread
+        uint4 rr[RPT];
+        if (!SWIGLU && p.resid != nullptr) {
 #pragma unroll
-        for (int qq = 0; qq < Q_PER_WARP; ++qq) {
-          const int q = chalf * Q_PER_WARP + qq;
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(acc_col0 + q * 32), r);
-          ptx::tmem_ld_wait();
-          float v[32];
+          for (int i = 0; i < RPT; ++i) {
+            const int idx = i * QT + tq;
+            const int rrow = idx >> 3, rchunk = idx & 7;
+            const int gm = m0 + ew * 32 + rrow, gc = out_col0 + rchunk * 8;
+            rr[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (gm < p.M && gc + 8 <= p.N)
+              rr[i] = __ldg(reinterpret_cast<const uint4*>(p.resid + static_cast<size_t>(gm) * p.ldr + gc));
+          }
+        }
+        // accumulators: issue the TMEM loads now, consume after the slab hand-shake
+        uint32_t r[NCH][16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rs;
+        for (int h = 0; h < NCH; ++h)
+          ptx::tmem_ld_32x16(tmem_acc + static_cast<uint32_t>(acc_col0 + cq * CPW + h * 16), r[h]);
+        // the TMA store issued from this slab two sub-tiles ago must have finished reading it
+        if (q_leader) ptx::tma_store_wait_read<1>();
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "n"(QT) : "memory");
+        if (!SWIGLU && p.resid != nullptr) {
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int idx = i * QT + tq;
+            const int rrow = idx >> 3, rchunk = idx & 7;
+            const uint32_t dst = slab + rrow * 128 + ((rchunk ^ (rrow & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(rr[i].x), "r"(rr[i].y),
+                         "r"(rr[i].z), "r"(rr[i].w)
+                         : "memory");
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "n"(QT) : "memory");
+        }
+        const uint32_t sbase = slab + lane * 128;  // this thread's row inside the slab
+        ptx::tmem_ld_wait();
 
+#pragma unroll
+        for (int h = 0; h < NCH; ++h) {
+          float v[16];
+          if (p.row_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[h][j]) * rs;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[h][j]);
+          }
           if constexpr (SWIGLU) {
-            // columns are (gate, up) pairs: 32 accumulators -> 16 outputs
-            uint32_t o[8];
+            // columns are (gate, up) pairs: 16 accumulators -> 8 outputs = one 16-byte chunk
+            uint32_t o[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               const float a0 = silu_fast(v[4 * j]) * v[4 * j + 1];
               const float a1 = silu_fast(v[4 * j + 2]) * v[4 * j + 3];
               o[j] = pack_bf16(a0, a1);
             }
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int chunk = 2 * q + c;
-              const uint32_t dst = sbase + ((chunk ^ (row & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[4 * c]),
-                           "r"(o[4 * c + 1]), "r"(o[4 * c + 2]), "r"(o[4 * c + 3])
-                           : "memory");
-            }
+            const int chunk = 2 * cq + h;
+            const uint32_t dst = sbase + ((chunk ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]),
+                         "r"(o[2]), "r"(o[3])
+                         : "memory");
           } else {
-            const int nb = n0 + acc_col0 + q * 32;  // global column of v[0]
+            const int nb = n0 + acc_col0 + cq * CPW + h * 16;  // global column of v[0]
             if (p.bias != nullptr) {
-              if (nb + 32 <= p.N) {
+              if (nb + 16 <= p.N) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 4; ++j) {
                   const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j);
                   v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
                 }
               } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
+                for (int j = 0; j < 16; ++j)
                   if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
               }
             }
-            if (p.act == ACT_GELU) {
+            if (p.act == ACT_GELU_HALF) {
+              gelu_half_hybrid(v);
+            } else if (p.act == ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+              for (int j = 0; j < 16; ++j) v[j] *= 0.5f;
+              gelu_half_hybrid(v);
             } else if (p.act == ACT_SILU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
+              for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
             }
-            if (p.resid != nullptr && row_ok) {
-              const __nv_bfloat16* rp = p.resid + static_cast<size_t>(m) * p.ldr + nb;
-              if (nb + 32 <= p.N) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(rp) + j);
-                  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+            for (int c = 0; c < 2; ++c) {
+              const int chunk = (cq * CPW + h * 16) / 8 + c;
+              const uint32_t dst = sbase + ((chunk ^ (lane & 7)) << 4);
+              if (p.resid != nullptr) {  // residual already sits at this slot (own row: no cross-lane hazard)
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                             : "r"(dst));
+                const uint32_t w[4] = {w0, w1, w2, w3};
 #pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    v[8 * j + 2 * t] += __uint_as_float(w[t] << 16);
-                    v[8 * j + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
-                  }
+                for (int t = 0; t < 4; ++t) {
+                  v[8 * c + 2 * t] += __uint_as_float(w[t] << 16);
+                  v[8 * c + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
                 }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (nb + j < p.N) v[j] += __bfloat162float(rp[j]);
               }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int chunk = 4 * q + c;
-              const uint32_t dst = sbase + ((chunk ^ (row & 7)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
                            "r"(pack_bf16(v[8 * c], v[8 * c + 1])),
                            "r"(pack_bf16(v[8 * c + 2], v[8 * c + 3])),
@@ -305,9 +360,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
         ptx::fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (store_leader) {
-          ptx::tma_store_2d(&tmap_d, out_col0, m0, smem_stage0 + sbuf * STAGING_BYTES);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "n"(QT) : "memory");
+        if (q_leader) {
+          ptx::tma_store_2d(&tmap_d, out_col0, m0 + ew * 32, slab);
           ptx::tma_store_commit();
         }
         sbuf ^= 1;
@@ -317,7 +372,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       ptx::mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (store_leader) ptx::tma_store_wait<0>();
+    if (q_leader) ptx::tma_store_wait<0>();
   }
 
   ptx::tc_fence_before();
@@ -385,7 +440,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if (int rc = make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, BLOCK_M)) return rc;
   if (int rc = make_tmap_bf16(&tw, g.W, g.N, g.K, g.ldw, BLOCK_N)) return rc;
   const int n_out = SWIGLU ? g.N / 2 : g.N;
-  if (int rc = make_tmap_bf16(&td, g.D, g.M, n_out, g.ldd, BLOCK_M)) return rc;
+  if (int rc = make_tmap_bf16(&td, g.D, g.M, n_out, g.ldd, 32)) return rc;  // per-quarter 32-row stores
   EpiParams ep;
   ep.M = g.M; ep.N = g.N; ep.K = g.K;
   ep.bias = g.bias; ep.row_scale = g.row_scale;

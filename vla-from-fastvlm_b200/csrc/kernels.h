@@ -92,6 +92,9 @@ int embed_splice(int dtype, const void* table, const void* img_feats, int n_img,
 int pool_norm(int dtype, const void* hidden, const float* norm_w, const int* pool_idx,
               const int* lens, int mode, float* pooled, int B, int T, int H, float eps,
               cudaStream_t stream);
+// rotate-half RoPE in place on the first `heads` head slices (q heads then k heads) of the qkv rows
+int rope_inplace(int dtype, void* qkv, int ld, int B, int n_tok, int heads, int head_dim,
+                 const float* cos_t, const float* sin_t, cudaStream_t s);
 int swiglu_interleaved(int dtype, const void* gu, void* out, int rows, int I, cudaStream_t stream);
 
 // ---- FastVLA action head (fastvla/fastvlm_with_expert.py:23-38, 50-54) ------------------------

@@ -109,6 +109,37 @@ __global__ void swiglu_kernel(const T* __restrict__ gu, T* __restrict__ out, lon
   r.store(out + idx * 8);
 }
 
+// Rotate-half RoPE applied in place to the q and k head slices of the fused qkv buffer
+// (transformers apply_rotary_pos_emb; position = row index inside the sample).  One thread rotates 8
+// (lo, hi) pairs of one head of one token, so attention can stage K/V with plain 16-byte copies.
+template <typename T>
+__global__ void rope_inplace_kernel(T* __restrict__ qkv, int ld, int n_tok, int heads, int hd,
+                                    const float* __restrict__ cs, const float* __restrict__ sn,
+                                    long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int half = hd >> 1, vpr = half >> 3;
+  const int v = static_cast<int>(idx % vpr);
+  const int h = static_cast<int>((idx / vpr) % heads);
+  const long long row = idx / (static_cast<long long>(vpr) * heads);
+  const int pos = static_cast<int>(row % n_tok);
+  T* p = qkv + row * ld + h * hd + v * 8;
+  Vec8<T> lo, hi;
+  lo.load(p);
+  hi.load(p + half);
+  const float* c = cs + static_cast<size_t>(pos) * half + v * 8;
+  const float* s = sn + static_cast<size_t>(pos) * half + v * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float co = __ldg(c + j), si = __ldg(s + j);
+    const float a = lo.v[j], b = hi.v[j];
+    lo.v[j] = a * co - b * si;
+    hi.v[j] = b * co + a * si;
+  }
+  lo.store(p);
+  hi.store(p + half);
+}
+
 template <typename TS, typename TD>
 __global__ void convert_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -201,6 +232,21 @@ int convert(int sd, const void* src, int dd, void* dst, long long n, cudaStream_
   else if (sd == DT_U8 && dd == DT_BF16) FVLA_CVT(uint8_t, __nv_bfloat16);
   else { set_error("convert: unsupported dtype pair"); return 2; }
 #undef FVLA_CVT
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int rope_inplace(int dtype, void* qkv, int ld, int B, int n_tok, int heads, int head_dim,
+                 const float* cos_t, const float* sin_t, cudaStream_t s) {
+  FVLA_REQUIRE(head_dim % 16 == 0 && ld % 8 == 0, "rope: head_dim % 16, pitch % 8");
+  const long long total = static_cast<long long>(B) * n_tok * heads * (head_dim / 16);
+  const unsigned blocks = static_cast<unsigned>(ceil_div_ll(total, 256));
+  if (dtype == DT_F32)
+    rope_inplace_kernel<float><<<blocks, 256, 0, s>>>(static_cast<float*>(qkv), ld, n_tok, heads, head_dim,
+                                                      cos_t, sin_t, total);
+  else
+    rope_inplace_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(static_cast<__nv_bfloat16*>(qkv), ld, n_tok,
+                                                              heads, head_dim, cos_t, sin_t, total);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
