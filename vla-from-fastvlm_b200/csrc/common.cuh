@@ -46,6 +46,20 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+// Output-side GELU of the NHWC kernels: exact erf form when activations are stored in fp32 (parity
+// mode); for bf16 storage the tanh form with the polynomial fitted to erf (|err| <= 2.5e-5 + 2^-11 rel,
+// see gemm_sm100.cu) — a quarter of the instructions of erff.
+__device__ __forceinline__ float gelu_tanh_fit(float x) {
+  const float u = fminf(x * x, 64.0f);
+  const float q = fmaf(u, fmaf(u, -3.51516789e-04f, 3.70056460e-02f), 7.97507884e-01f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * q));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+template <typename T> __device__ __forceinline__ float gelu_store(float x);
+template <> __device__ __forceinline__ float gelu_store<float>(float x) { return gelu_erf(x); }
+template <> __device__ __forceinline__ float gelu_store<__nv_bfloat16>(float x) { return gelu_tanh_fit(x); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float silu_precise(float x) { return x / (1.0f + expf(-x)); }
 

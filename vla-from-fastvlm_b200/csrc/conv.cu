@@ -173,7 +173,7 @@ stem_conv_kernel(const T* __restrict__ in, const float* __restrict__ w,
     if (ox >= Wo) continue;
     Vec8<T> r;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) r.v[c] = gelu_erf(acc[o][c]);
+    for (int c = 0; c < 8; ++c) r.v[c] = gelu_store<T>(acc[o][c]);
     r.store(out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * Cout + co0);
   }
 }
@@ -269,7 +269,11 @@ dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w,
     if (ox >= Wo) continue;
     Vec8<T> r;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) r.v[c] = act == ACT_GELU ? gelu_erf(acc[o][c]) : acc[o][c];
+    for (int c = 0; c < 8; ++c) r.v[c] = acc[o][c];
+    if (act == ACT_GELU) {  // uniform branch: the activation must not be evaluated when unused
+#pragma unroll
+      for (int c = 0; c < 8; ++c) r.v[c] = gelu_store<T>(r.v[c]);
+    }
     r.store(out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * Cout + co0);
   }
 }
@@ -453,10 +457,11 @@ int stem_conv3x3_s2(int dtype, const void* in, const float* w_packed, const floa
 }
 
 int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, void* out, int B,
-           int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream) {
+           int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream,
+           const float* w_host, const float* b_host) {
   FVLA_REQUIRE((Cin * mult) % 8 == 0, "dwconv: output channels must be a multiple of 8");
   if (dwconv_tiled_supported(dtype, H, W, Cin, mult, ksize, stride))
-    return dwconv_tiled(in, w_packed, bias, out, B, H, W, Cin, ksize, act, stream);
+    return dwconv_tiled(in, w_packed, bias, out, B, H, W, Cin, ksize, act, stream, w_host, b_host);
   if (dtype == DT_F32)
     return dwconv_dispatch<float>(in, w_packed, bias, out, B, H, W, Cin, mult, ksize, stride, act, stream);
   return dwconv_dispatch<__nv_bfloat16>(in, w_packed, bias, out, B, H, W, Cin, mult, ksize, stride, act, stream);

@@ -5,7 +5,9 @@ parity tests run on random weights of the real architecture.  The init is delibe
 non-degenerate (SURVEY.md trap T5): FastViT's default layer-scale (1e-5) and identity BatchNorm
 would hide residual-branch bugs and HF's std-0.02 init makes attention uniform, so layer scales are
 O(0.3), BatchNorm statistics/affines, every bias and every norm weight are randomised, and matrices
-use 1/sqrt(fan_in) so activations stay O(1) at every tap.
+use 1/sqrt(fan_in) with residual-branch gains tuned so activations stay O(1) at every tap of the
+FULL-DEPTH tower (2/12/24/4/2 blocks) — otherwise the late attention stages see one-hot softmaxes and the
+whole forward becomes chaotically sensitive to rounding (measured; see scripts/parity_fullsize.py).
 
 Keys are those of `LlavaQwen2ForCausalLM.state_dict()`; head keys are those of
 `FastVLMWithExpert` (src/vla_fastvlm/fastvla/fastvlm_with_expert.py:23-38).
@@ -63,16 +65,16 @@ def synthetic_backbone_state_dict(arch: "BackboneArch", seed: int = 0) -> Dict[s
         hd = d * v.mlp_ratio
         sd[base + ".convffn.conv.conv.weight"] = r.normal(d, 1, 7, 7, std=1.0 / 7)
         r.bn(sd, base + ".convffn.conv.bn", d)
-        sd[base + ".convffn.fc1.weight"] = r.linear(hd, d, 1.4).view(hd, d, 1, 1)
+        sd[base + ".convffn.fc1.weight"] = r.linear(hd, d, 1.2).view(hd, d, 1, 1)
         sd[base + ".convffn.fc1.bias"] = r.normal(hd, std=0.1)
-        sd[base + ".convffn.fc2.weight"] = r.linear(d, hd, 1.4).view(d, hd, 1, 1)
+        sd[base + ".convffn.fc2.weight"] = r.linear(d, hd, 1.2).view(d, hd, 1, 1)
         sd[base + ".convffn.fc2.bias"] = r.normal(d, std=0.1)
 
     idx = 0
     for i, d in enumerate(v.dims):
         if v.pos_emb[i]:
             # RepCPE reparameterised: depthwise 7x7 of pe(x) + x  -> identity tap + perturbation
-            w = r.normal(d, 1, 7, 7, std=0.3 / 7)
+            w = r.normal(d, 1, 7, 7, std=0.15 / 7)
             w[:, 0, 3, 3] += 1.0
             sd[P + f"network.{idx}.reparam_conv.weight"] = w
             sd[P + f"network.{idx}.reparam_conv.bias"] = r.normal(d, std=0.05)
@@ -81,26 +83,28 @@ def synthetic_backbone_state_dict(arch: "BackboneArch", seed: int = 0) -> Dict[s
             base = P + f"network.{idx}.{j}"
             if v.attention[i]:
                 r.bn(sd, base + ".norm", d)
-                sd[base + ".token_mixer.qkv.weight"] = r.linear(3 * d, d, 1.0)
+                # q/k gains chosen so softmax logits have std ~2 (not one-hot, not uniform) on O(0.2) inputs
+                sd[base + ".token_mixer.qkv.weight"] = torch.cat(
+                    [r.linear(d, d, 7.0), r.linear(d, d, 7.0), r.linear(d, d, 3.0)], dim=0)
                 sd[base + ".token_mixer.proj.weight"] = r.linear(d, d, 1.0)
                 sd[base + ".token_mixer.proj.bias"] = r.normal(d, std=0.1)
-                sd[base + ".layer_scale_1"] = r.uniform(d, 1, 1, lo=0.2, hi=0.6)
-                sd[base + ".layer_scale_2"] = r.uniform(d, 1, 1, lo=0.2, hi=0.6)
+                sd[base + ".layer_scale_1"] = r.uniform(d, 1, 1, lo=0.1, hi=0.3)
+                sd[base + ".layer_scale_2"] = r.uniform(d, 1, 1, lo=0.1, hi=0.3)
             else:
                 # RepMixer reparameterised: x + ls*(mixer(x) - norm(x)) as one depthwise 3x3
-                w = r.normal(d, 1, 3, 3, std=0.3 / 3)
-                w[:, 0, 1, 1] += 1.0
+                w = r.normal(d, 1, 3, 3, std=0.1 / 3)
+                w[:, 0, 1, 1] += 0.97
                 sd[base + ".token_mixer.reparam_conv.weight"] = w
                 sd[base + ".token_mixer.reparam_conv.bias"] = r.normal(d, std=0.05)
-                sd[base + ".layer_scale"] = r.uniform(d, 1, 1, lo=0.2, hi=0.6)
+                sd[base + ".layer_scale"] = r.uniform(d, 1, 1, lo=0.1, hi=0.3)
             convffn(base, d)
         idx += 1
         if i + 1 < len(v.dims):
             d2 = v.dims[i + 1]
             base = P + f"network.{idx}"
-            sd[base + ".proj.0.lkb_reparam.weight"] = r.normal(d2, 1, 7, 7, std=1.2 / 7)
+            sd[base + ".proj.0.lkb_reparam.weight"] = r.normal(d2, 1, 7, 7, std=1.0 / 7)
             sd[base + ".proj.0.lkb_reparam.bias"] = r.normal(d2, std=0.1)
-            sd[base + ".proj.1.reparam_conv.weight"] = r.linear(d2, d2, 1.5).view(d2, d2, 1, 1)
+            sd[base + ".proj.1.reparam_conv.weight"] = r.linear(d2, d2, 1.3).view(d2, d2, 1, 1)
             sd[base + ".proj.1.reparam_conv.bias"] = r.normal(d2, std=0.1)
             idx += 1
     ce, cr = v.out_channels, v.se_reduced
