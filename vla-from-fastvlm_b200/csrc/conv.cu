@@ -457,11 +457,10 @@ int stem_conv3x3_s2(int dtype, const void* in, const float* w_packed, const floa
 }
 
 int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, void* out, int B,
-           int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream,
-           const float* w_host, const float* b_host) {
+           int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream) {
   FVLA_REQUIRE((Cin * mult) % 8 == 0, "dwconv: output channels must be a multiple of 8");
   if (dwconv_tiled_supported(dtype, H, W, Cin, mult, ksize, stride))
-    return dwconv_tiled(in, w_packed, bias, out, B, H, W, Cin, ksize, act, stream, w_host, b_host);
+    return dwconv_tiled(in, w_packed, bias, out, B, H, W, Cin, ksize, act, stream);
   if (dtype == DT_F32)
     return dwconv_dispatch<float>(in, w_packed, bias, out, B, H, W, Cin, mult, ksize, stride, act, stream);
   return dwconv_dispatch<__nv_bfloat16>(in, w_packed, bias, out, B, H, W, Cin, mult, ksize, stride, act, stream);

@@ -131,129 +131,6 @@ dwconv_tiled_kernel(const __nv_bfloat16* __restrict__ in, const float* __restric
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Variant with the weights in the kernel-parameter (constant) bank.
-// The kernel above spends half of its shared-memory bandwidth re-reading the 7 weight vectors of a
-// kernel row, and the 56 weight registers cap it at one CTA per SM.  Here every lane of a warp works
-// on the SAME 8 channels (warp = 4 rows x 8 pixel groups of one channel vector), so a tap's weight is
-// warp-uniform and the FFMA takes it straight from the constant bank: no LDS, no weight registers.
-// Up to CWMAX channels' weights travel as a __grid_constant__ parameter (25.6 KB for 7x7); wider
-// layers are issued as several launches over channel ranges.
-// ---------------------------------------------------------------------------------------------
-constexpr int CWMAX = 128;
-template <int K> struct DwParamBlock {
-  float w[K * K][CWMAX];
-  float bias[CWMAX];
-};
-
-template <int K>
-__global__ void __launch_bounds__(256, 2)
-dwconv_tiled_cw_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int H, int W,
-                       int C, int c_base, int act, const __grid_constant__ DwParamBlock<K> prm) {
-  using G = TileGeom<K>;
-  constexpr int PAD = K / 2;
-  extern __shared__ __align__(16) uint8_t smem_dw[];
-  const uint32_t s_in = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dw));
-
-  const int tiles_x = W / TW;
-  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-  const int cl0 = blockIdx.y * CB;            // first channel of this CTA inside the parameter block
-  const int c0 = c_base + cl0;                // ... and in the tensor
-  const int b = blockIdx.z;
-  const int x0 = tx * TW, y0 = ty * TH;
-  const int tid = threadIdx.x;
-
-  const __nv_bfloat16* img = in + static_cast<size_t>(b) * H * W * C + c0;
-  for (int idx = tid; idx < G::IH * G::IW * 4; idx += 256) {
-    const int cv = idx & 3;
-    const int xi = (idx >> 2) % G::IW;
-    const int r = (idx >> 2) / G::IW;
-    const int gy = y0 + r - PAD, gx = x0 + xi - PAD;
-    const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-    const __nv_bfloat16* src = ok ? img + (static_cast<size_t>(gy) * W + gx) * C + cv * 8 : img;
-    const uint32_t dst = s_in + static_cast<uint32_t>(((r * 4 + cv) * G::XP + xi + (xi >> 3)) * 16);
-    cp_async16(dst, src, ok ? 16 : 0);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-
-  // warp = (row group of 4, channel vector); lane = (row in group, 8-pixel group)
-  const int warp = tid >> 5, lane = tid & 31;
-  const int cv = warp >> 1;                        // warp-uniform
-  const int row = (warp & 1) * 4 + (lane >> 3);
-  const int pg = lane & 7;
-  const int cw = cl0 + cv * 8;                     // warp-uniform offset into the parameter block
-  float acc[8][8];
-#pragma unroll
-  for (int o = 0; o < 8; ++o)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[o][c] = prm.bias[cw + c];
-
-#pragma unroll 1
-  for (int ky = 0; ky < K; ++ky) {
-    const uint32_t line = s_in + static_cast<uint32_t>((((row + ky) * 4 + cv) * G::XP) * 16);
-    const float* wrow = &prm.w[ky * K][cw];        // constant bank, uniform address
-#pragma unroll
-    for (int i = 0; i < 8 + K - 1; ++i) {
-      const int xi = pg * 8 + i;
-      uint4 raw;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
-                   : "r"(line + static_cast<uint32_t>((xi + (xi >> 3)) * 16)));
-      float x[8];
-      x[0] = __uint_as_float(raw.x << 16); x[1] = __uint_as_float(raw.x & 0xffff0000u);
-      x[2] = __uint_as_float(raw.y << 16); x[3] = __uint_as_float(raw.y & 0xffff0000u);
-      x[4] = __uint_as_float(raw.z << 16); x[5] = __uint_as_float(raw.z & 0xffff0000u);
-      x[6] = __uint_as_float(raw.w << 16); x[7] = __uint_as_float(raw.w & 0xffff0000u);
-#pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        const int kx = i - o;
-        if (kx < 0 || kx >= K) continue;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[o][c] = fmaf(x[c], wrow[kx * CWMAX + c], acc[o][c]);
-      }
-    }
-  }
-  __nv_bfloat16* orow =
-      out + ((static_cast<size_t>(b) * H + (y0 + row)) * W + x0 + pg * 8) * C + c0 + cv * 8;
-#pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    Vec8<__nv_bfloat16> r;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) r.v[c] = acc[o][c];
-    if (act == ACT_GELU) {  // uniform branch: the activation must not be evaluated when unused
-#pragma unroll
-      for (int c = 0; c < 8; ++c) r.v[c] = gelu_tanh_fit(r.v[c]);
-    }
-    r.store(orow + static_cast<size_t>(o) * C);
-  }
-}
-
-template <int K>
-int launch_tiled_cw(const void* in, const float* w_host, const float* b_host, void* out, int B, int H, int W,
-                    int C, int act, cudaStream_t stream) {
-  using G = TileGeom<K>;
-  auto kfn = dwconv_tiled_cw_kernel<K>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G::IN_BYTES));
-    attr_set = true;
-  }
-  for (int c_base = 0; c_base < C; c_base += CWMAX) {
-    const int nc = C - c_base < CWMAX ? C - c_base : CWMAX;
-    DwParamBlock<K> prm;
-    for (int t = 0; t < K * K; ++t)
-      for (int c = 0; c < CWMAX; ++c) prm.w[t][c] = c < nc ? w_host[static_cast<size_t>(t) * C + c_base + c] : 0.f;
-    for (int c = 0; c < CWMAX; ++c) prm.bias[c] = c < nc ? b_host[c_base + c] : 0.f;
-    dim3 grid((W / TW) * (H / TH), nc / CB, B);
-    kfn<<<grid, 256, G::IN_BYTES, stream>>>(static_cast<const __nv_bfloat16*>(in),
-                                            static_cast<__nv_bfloat16*>(out), H, W, C, c_base, act, prm);
-    FVLA_CUDA_CHECK(cudaGetLastError());
-  }
-  return 0;
-}
-
 template <int K>
 int launch_tiled(const void* in, const float* w, const float* bias, void* out, int B, int H, int W,
                  int C, int act, cudaStream_t stream) {
@@ -279,9 +156,7 @@ bool dwconv_tiled_supported(int dtype, int H, int W, int C, int mult, int k, int
 }
 
 int dwconv_tiled(const void* in, const float* w, const float* bias, void* out, int B, int H, int W,
-                 int C, int k, int act, cudaStream_t stream, const float* w_host, const float* b_host) {
-  if (w_host != nullptr && b_host != nullptr && k == 7)  // 7x7 is FMA/LDS-bound: constant-bank weights
-    return launch_tiled_cw<7>(in, w_host, b_host, out, B, H, W, C, act, stream);
+                 int C, int k, int act, cudaStream_t stream) {
   if (k == 7) return launch_tiled<7>(in, w, bias, out, B, H, W, C, act, stream);
   return launch_tiled<3>(in, w, bias, out, B, H, W, C, act, stream);
 }

@@ -259,8 +259,6 @@ int Engine::make_dw(DwW* d, const std::vector<float>& w, const std::vector<float
     for (int t = 0; t < k * k; ++t) packed[static_cast<size_t>(t) * cout + o] = w[static_cast<size_t>(o) * k * k + t];
   d->w = upload_f32(packed);
   d->bias = upload_f32(bias);
-  d->hw = packed;
-  d->hb = bias;
   FVLA_REQUIRE(d->w != nullptr && d->bias != nullptr, "cudaMalloc failed for a depthwise conv");
   d->cin = cin; d->mult = mult; d->k = k; d->stride = stride; d->act = act;
   return 0;
@@ -644,8 +642,7 @@ int Engine::run_dw(const DwW& w, const void* in, void* out, int B, int H, int W,
   const double fl = 2.0 * w.k * w.k * static_cast<double>(B) * Ho * Wo * w.cin * w.mult;
   flops += fl;
   prof_begin(s);
-  const int rc = dwconv(cfg.dtype, in, w.w, w.bias, out, B, H, W, w.cin, w.mult, w.k, w.stride, w.act, s,
-                        w.hw.data(), w.hb.data());
+  const int rc = dwconv(cfg.dtype, in, w.w, w.bias, out, B, H, W, w.cin, w.mult, w.k, w.stride, w.act, s);
   if (profile_) {
     const double e = static_cast<double>(esz());
     const double by = e * (static_cast<double>(B) * H * W * w.cin + static_cast<double>(B) * Ho * Wo * w.cin * w.mult) +

@@ -25,7 +25,6 @@ struct GemmW {  // packed nn.Linear / 1x1 conv
 struct DwW {  // packed depthwise / grouped conv
   float* w = nullptr;     // [k*k][Cout] fp32
   float* bias = nullptr;  // [Cout] fp32
-  std::vector<float> hw, hb;  // host copies (weights can ride in the kernel-parameter constant bank)
   int cin = 0, mult = 1, k = 3, stride = 1, act = 0;
 };
 struct VisBlock {

@@ -53,17 +53,13 @@ int stem_conv3x3_s2(int dtype, const void* in, const float* w_packed, const floa
 int stem_im2col_bf16(const void* in, void* col, int B, int H, int W, cudaStream_t stream);
 // Depthwise / grouped k x k conv, groups = Cin, Cout = mult*Cin (mult 1 or 2), pad k/2,
 // + bias (+ GELU).  w_packed: [k*k][Cout] fp32.
-// w_host / b_host: optional HOST copies of the same packed weights; when present the wide 7x7 layers run the
-// variant that feeds weights through the kernel-parameter constant bank (dwconv_tiled.cu)
 int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, void* out, int B,
-           int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream,
-           const float* w_host = nullptr, const float* b_host = nullptr);
+           int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream);
 
 // smem-tiled bf16 fast path (stride 1, mult 1, k in {3,7}, W%64==0, H%8==0, C%32==0); dwconv() uses it
 bool dwconv_tiled_supported(int dtype, int H, int W, int C, int mult, int k, int stride);
 int dwconv_tiled(const void* in, const float* w_packed, const float* bias, void* out, int B, int H,
-                 int W, int C, int k, int act, cudaStream_t stream, const float* w_host = nullptr,
-                 const float* b_host = nullptr);
+                 int W, int C, int k, int act, cudaStream_t stream);
 
 // ---- squeeze-excite tail of conv_exp ---------------------------------------------------------
 // x: [B, HW, C]; gate = sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2); out = gelu(x * gate)
