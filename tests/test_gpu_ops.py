@@ -255,6 +255,9 @@ ATTN_CASES = [
     (2, 100, 12, 2, 128, True, True),      # Qwen2-1.5B / 7B head_dim
     (1, 77, 4, 4, 32, False, False),       # ragged N
     (2, 19, 2, 1, 64, True, True),         # tiny test-model shape
+    (2, 272, 14, 2, 64, True, False),      # Qwen2-0.5B after in-place RoPE (v2 kernel, causal, ragged tail)
+    (1, 300, 12, 2, 128, True, False),     # head_dim 128, v2 kernel
+    (2, 130, 4, 4, 64, False, False),      # v2 kernel, non-causal with a 2-key tail tile
 ]
 
 

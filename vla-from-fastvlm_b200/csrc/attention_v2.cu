@@ -1,0 +1,265 @@
+// Flash attention, second version (bf16, no rotary: Qwen2's RoPE is applied in place by rope_inplace).
+//
+// Differences from flash_attn_bf16_kernel (attention.cu), all aimed at instructions per score —
+// with head_dim 32 a score gets only 128 tensor-core flops, so the softmax bookkeeping dominates:
+//   * 128 queries per CTA (8 warps x 16 rows): K/V tiles are staged half as often per query
+//   * K/V tiles double-buffered with cp.async (zero-fill past the sequence end)
+//   * Q and K fragments via ldmatrix.x4 instead of scalar 32-bit shared loads
+//   * the softmax scale is folded into one FFMA feeding ex2: p = 2^(s*c - m*c)
+//   * masking code only runs on tiles that need it (sequence tail, causal diagonal); warps whose rows
+//     lie entirely before a causal tile skip it
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fvla {
+namespace {
+
+constexpr int BQ2 = 128;
+constexpr int BKV2 = 64;
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pk2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void cpa16(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+// rows x HD tile -> padded smem (row pitch HD+8 elements), 16-byte cp.async, zero fill beyond n_tok
+template <int HD, int ROWS, int THREADS>
+__device__ __forceinline__ void stage_async(uint32_t dst, const __nv_bfloat16* src, int ld, int tok0, int n_tok) {
+  constexpr int VPR = HD / 8;
+  constexpr int LDSB = (HD + 8) * 2;
+  for (int i = threadIdx.x; i < ROWS * VPR; i += THREADS) {
+    const int r = i / VPR, c = i % VPR;
+    const bool ok = tok0 + r < n_tok;
+    const __nv_bfloat16* p = ok ? src + static_cast<size_t>(tok0 + r) * ld + c * 8 : src;
+    cpa16(dst + r * LDSB + c * 16, p, ok ? 16 : 0);
+  }
+}
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(256)
+flash_attn_v2_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                     const __nv_bfloat16* __restrict__ v, int ld, __nv_bfloat16* __restrict__ o, int ld_o,
+                     int N, int heads_q, int heads_kv, float scale_log2e) {
+  constexpr int LDS = HD + 8;          // elements
+  constexpr int LDSB = LDS * 2;        // bytes
+  constexpr int KV_TILE_B = BKV2 * LDSB;
+  extern __shared__ __align__(16) uint8_t smem_a2[];
+  const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smem_a2));
+  const uint32_t sK = sQ + BQ2 * LDSB;            // 2 stages
+  const uint32_t sV = sK + 2 * KV_TILE_B;         // 2 stages
+
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (heads_q / heads_kv);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const size_t row0 = static_cast<size_t>(b) * N;
+  const __nv_bfloat16* qp = q + row0 * ld + h * HD;
+  const __nv_bfloat16* kp = k + row0 * ld + hk * HD;
+  const __nv_bfloat16* vp = v + row0 * ld + hk * HD;
+
+  const int q0 = qb * BQ2;
+  int kv_blocks = (N + BKV2 - 1) / BKV2;
+  if (CAUSAL) kv_blocks = min(kv_blocks, (q0 + BQ2 + BKV2 - 1) / BKV2);
+
+  stage_async<HD, BQ2, 256>(sQ, qp, ld, q0, N);
+  stage_async<HD, BKV2, 256>(sK, kp, ld, 0, N);
+  stage_async<HD, BKV2, 256>(sV, vp, ld, 0, N);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // Q fragments (A operand) of this warp's 16 rows
+  uint32_t qf[HD / 16][4];
+  {
+    const uint32_t base = sQ + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDSB + (lane >> 4) * 16;
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) ldsm_x4(qf[ks], base + ks * 32);
+  }
+
+  float oacc[HD / 8][4];
+#pragma unroll
+  for (int j = 0; j < HD / 8; ++j) { oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY};  // running max of the RAW scores
+  float l_run[2] = {0.f, 0.f};
+  const int qrow = q0 + warp * 16 + g;      // this thread's rows: qrow and qrow + 8
+  const int wrow_max = q0 + warp * 16 + 15;
+
+  for (int kb = 0; kb < kv_blocks; ++kb) {
+    const int st = kb & 1;
+    if (kb + 1 < kv_blocks) {  // prefetch the next tile into the other stage
+      stage_async<HD, BKV2, 256>(sK + (st ^ 1) * KV_TILE_B, kp, ld, (kb + 1) * BKV2, N);
+      stage_async<HD, BKV2, 256>(sV + (st ^ 1) * KV_TILE_B, vp, ld, (kb + 1) * BKV2, N);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    const int key0 = kb * BKV2;
+    const bool skip = CAUSAL && key0 > wrow_max;  // every key of the tile lies after every row of the warp
+    if (!skip) {
+      const uint32_t kt = sK + st * KV_TILE_B, vt = sV + st * KV_TILE_B;
+      // ---- S = Q K^T ----
+      float s[BKV2 / 8][4];
+#pragma unroll
+      for (int j = 0; j < BKV2 / 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+      for (int j = 0; j < BKV2 / 8; j += 2) {
+        // matrices: (keys j*8.., dims ks*16..+7), (same keys, +8), (keys (j+1)*8.., ..), (.., +8)
+        const uint32_t kaddr = kt + ((j + (lane >> 4)) * 8 + (lane & 7)) * LDSB + ((lane >> 3) & 1) * 16;
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          uint32_t kf[4];
+          ldsm_x4(kf, kaddr + ks * 32);
+          mma16816(s[j], qf[ks], kf[0], kf[1]);
+          mma16816(s[j + 1], qf[ks], kf[2], kf[3]);
+        }
+      }
+      // ---- mask (only where needed) ----
+      const bool need_mask = (key0 + BKV2 > N) || (CAUSAL && key0 + BKV2 - 1 > q0 + warp * 16);
+      if (need_mask) {
+#pragma unroll
+        for (int j = 0; j < BKV2 / 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = key0 + j * 8 + 2 * tig + (e & 1);
+            const int qi = qrow + (e >> 1) * 8;
+            const bool dead = key >= N || (CAUSAL && key > qi);
+            if (dead) s[j][e] = -INFINITY;
+          }
+        }
+      }
+      // ---- online softmax ----
+      float mx[2] = {m_run[0], m_run[1]};
+#pragma unroll
+      for (int j = 0; j < BKV2 / 8; ++j) {
+        mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      }
+      float ms[2], corr[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float msafe = mx[r] == -INFINITY ? 0.f : mx[r];
+        ms[r] = msafe * scale_log2e;
+        corr[r] = ex2f(m_run[r] * scale_log2e - ms[r]);  // m_run = -inf -> 0
+        m_run[r] = mx[r];
+      }
+      float lsum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < BKV2 / 8; ++j) {
+        s[j][0] = ex2f(fmaf(s[j][0], scale_log2e, -ms[0]));
+        s[j][1] = ex2f(fmaf(s[j][1], scale_log2e, -ms[0]));
+        s[j][2] = ex2f(fmaf(s[j][2], scale_log2e, -ms[1]));
+        s[j][3] = ex2f(fmaf(s[j][3], scale_log2e, -ms[1]));
+        lsum[0] += s[j][0] + s[j][1];
+        lsum[1] += s[j][2] + s[j][3];
+      }
+      l_run[0] = fmaf(l_run[0], corr[0], lsum[0]);
+      l_run[1] = fmaf(l_run[1], corr[1], lsum[1]);
+#pragma unroll
+      for (int j = 0; j < HD / 8; ++j) {
+        oacc[j][0] *= corr[0]; oacc[j][1] *= corr[0];
+        oacc[j][2] *= corr[1]; oacc[j][3] *= corr[1];
+      }
+      // ---- O += P V ----
+#pragma unroll
+      for (int kk = 0; kk < BKV2 / 16; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pk2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pk2(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pk2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pk2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const uint32_t vaddr = vt + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDSB + (lane >> 4) * 16;
+#pragma unroll
+        for (int jn = 0; jn < HD / 8; jn += 2) {
+          uint32_t vb[4];
+          ldsm_x4_t(vb, vaddr + jn * 16);
+          mma16816(oacc[jn], pa, vb[0], vb[1]);
+          mma16816(oacc[jn + 1], pa, vb[2], vb[3]);
+        }
+      }
+    }
+    // next tile landed; everyone is done reading this stage before it is overwritten next iteration
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+
+  // ---- normalise and store ----
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
+  const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+  __nv_bfloat16* op = o + row0 * ld_o + h * HD;
+#pragma unroll
+  for (int j = 0; j < HD / 8; ++j) {
+    const int col = j * 8 + 2 * tig;
+    if (qrow < N)
+      *reinterpret_cast<uint32_t*>(op + static_cast<size_t>(qrow) * ld_o + col) =
+          pk2(oacc[j][0] * inv0, oacc[j][1] * inv0);
+    if (qrow + 8 < N)
+      *reinterpret_cast<uint32_t*>(op + static_cast<size_t>(qrow + 8) * ld_o + col) =
+          pk2(oacc[j][2] * inv1, oacc[j][3] * inv1);
+  }
+}
+
+template <int HD, bool CAUSAL>
+int launch_v2(const AttnArgs& a, cudaStream_t stream) {
+  auto kfn = flash_attn_v2_kernel<HD, CAUSAL>;
+  constexpr int SMEM = (BQ2 + 4 * BKV2) * (HD + 8) * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(a.N, BQ2), a.heads_q, a.B);
+  kfn<<<grid, 256, SMEM, stream>>>(static_cast<const __nv_bfloat16*>(a.q), static_cast<const __nv_bfloat16*>(a.k),
+                                   static_cast<const __nv_bfloat16*>(a.v), a.ld_qkv,
+                                   static_cast<__nv_bfloat16*>(a.o), a.ld_o, a.N, a.heads_q, a.heads_kv,
+                                   a.scale * 1.4426950408889634f);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+bool attention_v2_supported(const AttnArgs& a) {
+  return a.rope_cos == nullptr && (a.head_dim == 32 || a.head_dim == 64 || a.head_dim == 128);
+}
+
+int attention_v2(const AttnArgs& a, cudaStream_t stream) {
+  if (a.head_dim == 32) return a.causal ? launch_v2<32, true>(a, stream) : launch_v2<32, false>(a, stream);
+  if (a.head_dim == 64) return a.causal ? launch_v2<64, true>(a, stream) : launch_v2<64, false>(a, stream);
+  return a.causal ? launch_v2<128, true>(a, stream) : launch_v2<128, false>(a, stream);
+}
+
+}  // namespace fvla

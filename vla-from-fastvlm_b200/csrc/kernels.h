@@ -80,7 +80,10 @@ struct AttnArgs {
   const float* rope_sin = nullptr;
 };
 int attention(int dtype, const AttnArgs& a, cudaStream_t stream);       // bf16: mma.sync flash; f32: SIMT
-int attention_simt(int dtype, const AttnArgs& a, cudaStream_t stream);  // reference-grade SIMT for either dtype
+int attention_simt(int dtype, const AttnArgs& a, cudaStream_t stream);
+// bf16, no rotary: 128-query CTAs, cp.async double buffering, ldmatrix operands (attention_v2.cu)
+bool attention_v2_supported(const AttnArgs& a);
+int attention_v2(const AttnArgs& a, cudaStream_t stream);  // reference-grade SIMT for either dtype
 
 // ---- Qwen2 glue ------------------------------------------------------------------------------
 int rmsnorm(int dtype, const void* x, const float* weight, void* out, int rows, int H, float eps,
