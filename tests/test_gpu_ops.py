@@ -258,6 +258,7 @@ ATTN_CASES = [
     (2, 272, 14, 2, 64, True, False),      # Qwen2-0.5B after in-place RoPE (v2 kernel, causal, ragged tail)
     (1, 300, 12, 2, 128, True, False),     # head_dim 128, v2 kernel
     (2, 130, 4, 4, 64, False, False),      # v2 kernel, non-causal with a 2-key tail tile
+    (1, 600, 4, 2, 64, True, False),       # v2 kernel, causal (N >= 512)
 ]
 
 

@@ -7,8 +7,7 @@
 // channel-vector stride is = 2 (mod 8) 16-byte slots, so every quarter-warp LDS.128 hits 8 distinct
 // bank groups.  A warp owns one output row; lane = (channel vector, pixel group): each thread slides
 // an 8-pixel window across the row for its 8 channels, keeping one kernel row of weights in
-// registers — 49 FMAs per output with ~0.44 shared-memory loads per FMA-group instead of one global
-// load per tap.
+// registers.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -34,16 +33,51 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int sr
                : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed-half arithmetic.  A first version of this kernel unpacked bf16 to fp32 per tap and was
+// instruction-bound (ncu, profiles/r01_dwconv_k7_c192_ncu.txt: issue slots 64 % busy, FMA pipe 37 %,
+// ALU pipe 43 % — unpacking and shared-memory loads cost as many slots as the FMAs; 23 TFLOP/s).
+// Here the halo tile is converted ONCE to fp16 while it is staged (bf16 values are
+// exactly representable in fp16 inside its range; out-of-range values saturate), the weights are
+// kept as fp16, and the taps of two kernel rows are accumulated with HFMA2 (two channels per
+// instruction, no unpacking) before being flushed into the fp32 accumulators.  fp16 carries 3 more
+// mantissa bits than the bf16 output, so the <= 14-term partial sums add ~2^-11 relative error,
+// a quarter of the output rounding.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf16x2_to_f16x2_sat(uint32_t w) {
+  const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t hfma2_u(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t hmul2_u(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ float2 h2_to_f2(uint32_t h) {
+  float2 f;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n"
+      : "=f"(f.x), "=f"(f.y)
+      : "r"(h));
+  return f;
+}
+
 template <int K>
 __global__ void __launch_bounds__(256, 2)
-dwconv_tiled_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
-                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W,
-                    int C, int act) {
+dwconv_tiled_h_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W,
+                      int C, int act) {
   using G = TileGeom<K>;
   constexpr int PAD = K / 2;
   extern __shared__ __align__(16) uint8_t smem_dw[];
   const uint32_t s_in = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dw));
-  float* s_w = reinterpret_cast<float*>(smem_dw + G::IN_BYTES);
+  uint32_t* s_wh = reinterpret_cast<uint32_t*>(smem_dw + G::IN_BYTES);  // [K*K][CB/2] half2
 
   const int tiles_x = W / TW;
   const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
@@ -52,22 +86,46 @@ dwconv_tiled_kernel(const __nv_bfloat16* __restrict__ in, const float* __restric
   const int x0 = tx * TW, y0 = ty * TH;
   const int tid = threadIdx.x;
 
-  // ---- stage the halo tile (coalesced 64-byte runs per pixel) ----
+  // ---- stage the halo tile, converting bf16 -> fp16 (coalesced 64-byte runs per pixel) ----
   const __nv_bfloat16* img = in + static_cast<size_t>(b) * H * W * C + c0;
-  for (int idx = tid; idx < G::IH * G::IW * 4; idx += 256) {
-    const int cv = idx & 3;
-    const int xi = (idx >> 2) % G::IW;
-    const int r = (idx >> 2) / G::IW;
-    const int gy = y0 + r - PAD, gx = x0 + xi - PAD;
-    const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-    const __nv_bfloat16* src = ok ? img + (static_cast<size_t>(gy) * W + gx) * C + cv * 8 : img;
-    const uint32_t dst = s_in + static_cast<uint32_t>(((r * 4 + cv) * G::XP + xi + (xi >> 3)) * 16);
-    cp_async16(dst, src, ok ? 16 : 0);
+  constexpr int NV = G::IH * G::IW * 4;
+  constexpr int PER = (NV + 255) / 256;
+  uint4 stage[PER];
+#pragma unroll
+  for (int it = 0; it < PER; ++it) {
+    const int idx = tid + it * 256;
+    stage[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (idx < NV) {
+      const int cv = idx & 3;
+      const int xi = (idx >> 2) % G::IW;
+      const int r = (idx >> 2) / G::IW;
+      const int gy = y0 + r - PAD, gx = x0 + xi - PAD;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+        stage[it] = __ldg(reinterpret_cast<const uint4*>(img + (static_cast<size_t>(gy) * W + gx) * C + cv * 8));
+    }
   }
-  for (int idx = tid; idx < K * K * CB; idx += 256)
-    s_w[idx] = __ldg(w + static_cast<size_t>(idx / CB) * C + c0 + (idx % CB));
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  for (int idx = tid; idx < K * K * (CB / 2); idx += 256) {
+    const int t = idx / (CB / 2), cp = idx % (CB / 2);
+    const float w0 = __ldg(w + static_cast<size_t>(t) * C + c0 + 2 * cp);
+    const float w1 = __ldg(w + static_cast<size_t>(t) * C + c0 + 2 * cp + 1);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(w1), "f"(w0));
+    s_wh[idx] = r;
+  }
+#pragma unroll
+  for (int it = 0; it < PER; ++it) {
+    const int idx = tid + it * 256;
+    if (idx < NV) {
+      const int cv = idx & 3;
+      const int xi = (idx >> 2) % G::IW;
+      const int r = (idx >> 2) / G::IW;
+      const uint32_t dst = s_in + static_cast<uint32_t>(((r * 4 + cv) * G::XP + xi + (xi >> 3)) * 16);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(bf16x2_to_f16x2_sat(stage[it].x)),
+                   "r"(bf16x2_to_f16x2_sat(stage[it].y)), "r"(bf16x2_to_f16x2_sat(stage[it].z)),
+                   "r"(bf16x2_to_f16x2_sat(stage[it].w))
+                   : "memory");
+    }
+  }
   __syncthreads();
 
   // ---- compute: warp = output row, lane = (channel vector, 8-pixel group) ----
@@ -83,36 +141,46 @@ dwconv_tiled_kernel(const __nv_bfloat16* __restrict__ in, const float* __restric
       acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
     }
   }
+  uint32_t racc[8][4];  // packed fp16 partial sums of up to two kernel rows
 #pragma unroll 1
   for (int ky = 0; ky < K; ++ky) {
-    float wr[K][8];
+    uint32_t wr[K][4];
 #pragma unroll
     for (int kx = 0; kx < K; ++kx) {
-      const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ky * K + kx) * CB + cv * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ky * K + kx) * CB + cv * 8 + 4);
-      wr[kx][0] = w0.x; wr[kx][1] = w0.y; wr[kx][2] = w0.z; wr[kx][3] = w0.w;
-      wr[kx][4] = w1.x; wr[kx][5] = w1.y; wr[kx][6] = w1.z; wr[kx][7] = w1.w;
+      const uint4 wv = *reinterpret_cast<const uint4*>(s_wh + (ky * K + kx) * (CB / 2) + cv * 4);
+      wr[kx][0] = wv.x; wr[kx][1] = wv.y; wr[kx][2] = wv.z; wr[kx][3] = wv.w;
     }
+    const bool fresh = (ky & 1) == 0;  // first row of a pair: start the partial sums with a multiply
     const uint32_t line = s_in + static_cast<uint32_t>((((row + ky) * 4 + cv) * G::XP) * 16);
 #pragma unroll
     for (int i = 0; i < 8 + K - 1; ++i) {
       const int xi = pg * 8 + i;
-      uint4 raw;
+      uint32_t x[4];
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                   : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
                    : "r"(line + static_cast<uint32_t>((xi + (xi >> 3)) * 16)));
-      float x[8];
-      x[0] = __uint_as_float(raw.x << 16); x[1] = __uint_as_float(raw.x & 0xffff0000u);
-      x[2] = __uint_as_float(raw.y << 16); x[3] = __uint_as_float(raw.y & 0xffff0000u);
-      x[4] = __uint_as_float(raw.z << 16); x[5] = __uint_as_float(raw.z & 0xffff0000u);
-      x[6] = __uint_as_float(raw.w << 16); x[7] = __uint_as_float(raw.w & 0xffff0000u);
 #pragma unroll
       for (int o = 0; o < 8; ++o) {
         const int kx = i - o;
         if (kx < 0 || kx >= K) continue;
+        if (kx == 0 && fresh) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[o][c] = fmaf(x[c], wr[kx][c], acc[o][c]);
+          for (int c = 0; c < 4; ++c) racc[o][c] = hmul2_u(x[c], wr[0][c]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) racc[o][c] = hfma2_u(x[c], wr[kx][c], racc[o][c]);
+        }
       }
+    }
+    if (!fresh || ky == K - 1) {  // flush the pair into the fp32 accumulators
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float2 f = h2_to_f2(racc[o][c]);
+          acc[o][2 * c] += f.x;
+          acc[o][2 * c + 1] += f.y;
+        }
     }
   }
   // ---- store ----
@@ -123,7 +191,7 @@ dwconv_tiled_kernel(const __nv_bfloat16* __restrict__ in, const float* __restric
     Vec8<__nv_bfloat16> r;
 #pragma unroll
     for (int c = 0; c < 8; ++c) r.v[c] = acc[o][c];
-    if (act == ACT_GELU) {  // uniform branch: the activation must not be evaluated when unused
+    if (act == ACT_GELU) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) r.v[c] = gelu_tanh_fit(r.v[c]);
     }
@@ -132,18 +200,19 @@ dwconv_tiled_kernel(const __nv_bfloat16* __restrict__ in, const float* __restric
 }
 
 template <int K>
-int launch_tiled(const void* in, const float* w, const float* bias, void* out, int B, int H, int W,
-                 int C, int act, cudaStream_t stream) {
+int launch_tiled_h(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int C,
+                   int act, cudaStream_t stream) {
   using G = TileGeom<K>;
-  auto kfn = dwconv_tiled_kernel<K>;
+  auto kfn = dwconv_tiled_h_kernel<K>;
+  constexpr int SMEM = G::IN_BYTES + K * K * (CB / 2) * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   dim3 grid((W / TW) * (H / TH), C / CB, B);
-  kfn<<<grid, 256, G::SMEM, stream>>>(static_cast<const __nv_bfloat16*>(in), w, bias,
-                                      static_cast<__nv_bfloat16*>(out), H, W, C, act);
+  kfn<<<grid, 256, SMEM, stream>>>(static_cast<const __nv_bfloat16*>(in), w, bias,
+                                   static_cast<__nv_bfloat16*>(out), H, W, C, act);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -157,8 +226,8 @@ bool dwconv_tiled_supported(int dtype, int H, int W, int C, int mult, int k, int
 
 int dwconv_tiled(const void* in, const float* w, const float* bias, void* out, int B, int H, int W,
                  int C, int k, int act, cudaStream_t stream) {
-  if (k == 7) return launch_tiled<7>(in, w, bias, out, B, H, W, C, act, stream);
-  return launch_tiled<3>(in, w, bias, out, B, H, W, C, act, stream);
+  if (k == 7) return launch_tiled_h<7>(in, w, bias, out, B, H, W, C, act, stream);
+  return launch_tiled_h<3>(in, w, bias, out, B, H, W, C, act, stream);
 }
 
 }  // namespace fvla
