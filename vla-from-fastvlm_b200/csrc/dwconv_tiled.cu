@@ -1,8 +1,9 @@
 // Shared-memory tiled depthwise k x k convolution (stride 1) for the wide FastViTHD stages
-// (RepMixer 3x3 and ConvFFN 7x7 at 256^2 x 96, 128^2 x 192, 64^2 x 384): NHWC bf16 in/out, fp32 math.
+// (RepMixer 3x3 and ConvFFN 7x7 at 256^2 x 96, 128^2 x 192, 64^2 x 384): NHWC bf16 in/out, fp16 taps
+// flushed into fp32 accumulators.
 //
 // A CTA (8 warps) produces an 8-row x 64-pixel x 32-channel output tile.  The (8+k-1) x (64+k-1)
-// input halo tile is staged once with cp.async (zero-filled outside the image) in a
+// input halo tile is staged once (zero-filled outside the image, converted to fp16) in a
 // [row][channel-vector][x] layout whose x index is padded by one slot every 8 pixels and whose
 // channel-vector stride is = 2 (mod 8) 16-byte slots, so every quarter-warp LDS.128 hits 8 distinct
 // bank groups.  A warp owns one output row; lane = (channel vector, pixel group): each thread slides
@@ -24,14 +25,7 @@ template <int K> struct TileGeom {
   static constexpr int XP_RAW = IW + (IW >> 3) + 1;     // padded slots per (row, cvec) line
   static constexpr int XP = XP_RAW + ((2 - (XP_RAW & 7)) & 7);  // = 2 (mod 8)
   static constexpr int IN_BYTES = IH * 4 * XP * 16;
-  static constexpr int W_BYTES = K * K * CB * 4;
-  static constexpr int SMEM = IN_BYTES + W_BYTES;
 };
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
-               : "memory");
-}
 
 // ---------------------------------------------------------------------------------------------
 // Packed-half arithmetic.  A first version of this kernel unpacked bf16 to fp32 per tap and was
