@@ -166,6 +166,31 @@ def test_dwconv(native, dtype, k, stride, mult, act, B, H, W, C):
     _close(out, ref, BF16_TOL if dtype == torch.bfloat16 else F32_TOL, f"dwconv k{k}s{stride}m{mult}")
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 64), (1, 32, 32, 96), (2, 48, 64, 32), (1, 256, 256, 96),
+                                     (3, 16, 32, 160)])
+def test_dwconv7_tensor_core(native, B, H, W, C):
+    """Tensor-core (Toeplitz mma) depthwise 7x7: every tile geometry, image borders inside and between tiles,
+    per-channel distinct taps; checked against conv2d with the taps it actually multiplies (bf16)."""
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 1000 + H + W + C)
+    x = torch.randn(B, C, H, W, generator=g).to(dev)
+    w = (torch.randn(C, 1, 7, 7, generator=g) / 7).to(dev)
+    b = torch.randn(C, generator=g).to(dev)
+    xin = x.permute(0, 2, 3, 1).contiguous().bfloat16()
+    out = native.op_dwconv(xin, _pack_dw(w), b, 7, 1, 1, 0)
+    ref = F.conv2d(xin.float().permute(0, 3, 1, 2), w.bfloat16().float(), b, padding=3, groups=C).permute(0, 2, 3, 1)
+    _close(out, ref, 1.0 / 256, "dwconv7 tensor core (bf16 taps)")
+    ref32 = F.conv2d(xin.float().permute(0, 3, 1, 2), w, b, padding=3, groups=C).permute(0, 2, 3, 1)
+    _close(out, ref32, BF16_TOL, "dwconv7 tensor core (fp32 taps)")
+    # an impulse image reads the taps back exactly (bf16-rounded), flipped, at the right channel
+    imp = torch.zeros(1, H, W, C, device=dev, dtype=torch.bfloat16)
+    imp[0, H // 2, W // 2, :] = 1.0
+    o = native.op_dwconv(imp, _pack_dw(w), torch.zeros(C, device=dev), 7, 1, 1, 0).float()
+    patch = o[0, H // 2 - 3:H // 2 + 4, W // 2 - 3:W // 2 + 4, :]  # [7,7,C]
+    want = w.bfloat16().float()[:, 0].flip(1, 2).permute(1, 2, 0)
+    assert torch.equal(patch, want), "impulse response != taps"
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_stem_conv(native, dtype):
     dev = _dev()

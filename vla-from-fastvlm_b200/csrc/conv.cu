@@ -457,8 +457,27 @@ int stem_conv3x3_s2(int dtype, const void* in, const float* w_packed, const floa
 }
 
 int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, void* out, int B,
-           int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream) {
+           int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream,
+           const uint32_t* wtab) {
   FVLA_REQUIRE((Cin * mult) % 8 == 0, "dwconv: output channels must be a multiple of 8");
+  if (dwconv7_mma_supported(dtype, H, W, Cin, mult, ksize, stride, act)) {
+    if (wtab == nullptr) {
+      // op-level callers (tests, micro-benchmarks) pass only the fp32 taps: build the table into a scratch
+      // buffer on the same stream (the engine builds its tables once at finalize)
+      static uint32_t* scratch = nullptr;
+      static size_t scratch_bytes = 0;
+      const size_t need = dwconv7_wtab_bytes(Cin);
+      if (need > scratch_bytes) {
+        FVLA_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (scratch != nullptr) FVLA_CUDA_CHECK(cudaFree(scratch));
+        FVLA_CUDA_CHECK(cudaMalloc(&scratch, need));
+        scratch_bytes = need;
+      }
+      if (int rc = dwconv7_mma_prepare(w_packed, Cin, scratch, stream)) return rc;
+      wtab = scratch;
+    }
+    return dwconv7_mma(in, wtab, bias, out, B, H, W, Cin, stream);
+  }
   if (dwconv_tiled_supported(dtype, H, W, Cin, mult, ksize, stride))
     return dwconv_tiled(in, w_packed, bias, out, B, H, W, Cin, ksize, act, stream);
   if (dtype == DT_F32)

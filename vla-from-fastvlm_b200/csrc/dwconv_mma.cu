@@ -1,0 +1,348 @@
+// Depthwise 7x7 convolution (stride 1, pad 3) on the tensor cores — the ConvFFN / RepCPE conv of every
+// FastViTHD block (reference: HF-hub FastViTHD `convffn.conv` + folded BN).
+//
+// Why tensor cores for a depthwise conv: 49 MACs per output make the SIMT version issue-bound (ncu:
+// profiles/r01_dwconv_k7_c192_ncu.txt — FMA+ALU pipes saturated at ~1 TB/s, a sixth of HBM speed).  Per
+// channel the conv is   out[y][x] = sum_ky ( in[y+ky][x .. x+6] . w[ky][0..6] ),
+// i.e. for every kernel row a product of a [rows x 16] slice of the image with a banded 16 x 8 Toeplitz
+// matrix of that row's taps: one mma.sync.m16n8k16 per (kernel row, 16 rows x 8 outputs), 7 per 128 outputs
+// instead of 3136 scalar FMAs.  44 % of the multiplies hit structural zeros; the tensor pipe has >20x the
+// headroom, and the kernel becomes what it should be — bound by moving the feature map.
+//
+// The catch is layout: activations are NHWC (channel fastest) but an mma fragment wants, for ONE channel,
+// rows = image rows and 16-bit pairs along x.  The kernel therefore transposes on chip, both ways, with
+// matrix loads/stores instead of per-element shuffles:
+//
+//   TMA (4-D tensor map, SWIZZLE_64B, zero fill outside the image = the conv's zero padding)
+//     -> slab ring   [2 rows][TW+8 px][32 ch]                      natural NHWC order
+//   ldmatrix.x4.trans  (8 px x 8 ch tiles -> channel-major register pairs)  + 4 STS.32
+//     -> planes      [32 ch][22 rows][TW+8 px]  bf16               one image plane per channel
+//   ldmatrix.x4 (A fragments, rows interleaved even/odd so kernel row ky+1 reuses half of ky's tiles)
+//     + Toeplitz B fragments from a 9-word-per-kernel-row table -> 7*NB mma.sync per (channel, 16 x 8NB px)
+//   fp32 accumulators (+bias) -> bf16 -> output planes -> LDS.32 + stmatrix.x4.trans
+//     -> staging     [16 rows][TW px][32 ch]  (swizzled)           natural NHWC order
+//   TMA store.
+//
+// CTA = 256 threads, tile = 16 rows x TW px x 32 channels, ~98 KB of shared memory -> 2 CTAs per SM so one
+// CTA's loads/stores overlap the other's math.  Algorithmic traffic: read + write the map once
+// (4 B per output element in bf16); the halo re-reads (22 x 40 / 16 x 32 = 1.7x) are served by L2.
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx_sm100.cuh"
+#include "tma_host.h"
+
+namespace fvla {
+namespace {
+
+constexpr int CB = 32;            // channels per CTA (64 B per pixel: one swizzle-64 row)
+constexpr int TH = 16;            // output rows per CTA (one mma M tile)
+constexpr int IH = TH + 6;        // input rows incl. halo
+constexpr int NSLAB = IH / 2;     // TMA slabs of two rows
+constexpr int RING = 6;           // slabs in flight
+constexpr int WTAB_WORDS = 64;    // Toeplitz table words per channel (7 kernel rows x 9, padded)
+constexpr int OROW_W = 18;        // output-plane row pitch in words (conflict-free D-fragment stores)
+constexpr int OPLANE_W = 292;     // words an output plane needs (16 * 18 = 288, +4: = 4 (mod 8))
+constexpr int THREADS = 256;
+
+template <int NB> struct Geo {
+  static constexpr int TW = 8 * NB;               // output pixels per tile row
+  static constexpr int IW = TW + 8;               // staged input pixels per row (16-wide k chunks reach 8 past)
+  static constexpr int XB = IW / 8;               // 8-pixel blocks per staged row
+  static constexpr int ROW_B = IW * 2;            // plane row pitch (bytes): an odd number of 16-byte units
+  static constexpr int PLANE_RAW_W = IH * ROW_B / 4;
+  static constexpr int PLANE_IN_W = PLANE_RAW_W + ((4 - (PLANE_RAW_W & 7)) & 7);  // = 4 (mod 8) words
+  // a channel's output plane overwrites its own input plane (only one warp ever reads it), so one pitch
+  static constexpr int PLANE_W = PLANE_IN_W > OPLANE_W ? PLANE_IN_W : OPLANE_W;
+  static constexpr int PLANE_B = PLANE_W * 4;
+  static constexpr int SLAB_B = 2 * IW * 64;
+  static constexpr int OUT_B = TH * TW * 64;
+  static constexpr int RING_B = (RING * SLAB_B > OUT_B) ? RING * SLAB_B : OUT_B;
+  static constexpr int PLANES_B = CB * PLANE_B;
+  static constexpr int WTAB_B = CB * WTAB_WORDS * 4;
+  static constexpr int BAR_B = 128;
+  static constexpr int SMEM_B = RING_B + PLANES_B + WTAB_B + BAR_B + 1024;
+  static_assert((ROW_B / 16) % 2 == 1, "plane rows must be an odd number of 16-byte units");
+  static_assert(SLAB_B % 512 == 0, "slabs must keep the 64-byte swizzle phase");
+  static_assert(PLANE_W % 8 == 4, "plane pitch must be 4 (mod 8) words");
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+      "[%6];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void stsm_x4_trans(uint32_t addr, const uint32_t (&r)[4]) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// physical plane row of tile-local input row y: even rows first, then odd rows, so that the eight rows
+// {2r + j} an A-fragment tile needs are consecutive (conflict-free ldmatrix) for either parity of j
+__device__ __forceinline__ int plane_row(int y) { return (y & 1) * (IH / 2) + (y >> 1); }
+
+template <int NB>
+__global__ void __launch_bounds__(THREADS, 2)
+dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
+                   const uint32_t* __restrict__ wtab, const float* __restrict__ bias, int tiles_x, int n_cblk) {
+  using G = Geo<NB>;
+  extern __shared__ uint8_t smem_dwm[];
+  const uint32_t base = (ptx::smem_u32(smem_dwm) + 1023u) & ~1023u;
+  const uint32_t ring = base;
+  const uint32_t planes = ring + G::RING_B;
+  const uint32_t s_wtab = planes + G::PLANES_B;
+  const uint32_t bars = s_wtab + G::WTAB_B;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  const uint32_t wbar = bars + 8u * NSLAB;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int cblk = blockIdx.x % n_cblk;
+  const int tile = blockIdx.x / n_cblk;
+  const int x0 = (tile % tiles_x) * G::TW, y0 = (tile / tiles_x) * TH;
+  const int c0 = cblk * CB;
+  const int b = blockIdx.y;
+
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tmap_in);
+    ptx::prefetch_tmap(&tmap_out);
+    for (int s = 0; s <= NSLAB; ++s) ptx::mbar_init(bars + 8u * s, 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    ptx::mbar_arrive_expect_tx(wbar, G::WTAB_B);
+    bulk_g2s(s_wtab, wtab + static_cast<size_t>(c0) * WTAB_WORDS, G::WTAB_B, wbar);
+#pragma unroll
+    for (int s = 0; s < RING; ++s) {
+      ptx::mbar_arrive_expect_tx(full_bar(s), G::SLAB_B);
+      tma_load_4d(ring + s * G::SLAB_B, &tmap_in, c0, x0 - 3, y0 - 3 + 2 * s, b, full_bar(s));
+    }
+  }
+
+  // ---- NHWC slabs -> per-channel planes ----
+  for (int s = warp; s < NSLAB; s += THREADS / 32) {
+    const int buf = s % RING;
+    ptx::mbar_wait(full_bar(s), 0);
+    const uint32_t slab = ring + buf * G::SLAB_B;
+#pragma unroll
+    for (int task = 0; task < 2 * G::XB; ++task) {
+      const int r = task / G::XB, xb = task % G::XB;
+      const int px = r * G::IW + xb * 8 + (lane & 7);
+      const int cv = lane >> 3;
+      uint32_t R[4];
+      ldsm_x4_trans(R, slab + px * 64 + ((cv ^ ((px >> 1) & 3)) << 4));
+      const int y = 2 * s + r;
+      const uint32_t dst = planes + g * G::PLANE_B + plane_row(y) * G::ROW_B + (xb * 4 + t) * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sts32(dst + q * 8 * G::PLANE_B, R[q]);
+    }
+    if (s + RING < NSLAB) {
+      __syncwarp();
+      if (lane == 0) {
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive_expect_tx(full_bar(s + RING), G::SLAB_B);
+        tma_load_4d(slab, &tmap_in, c0, x0 - 3, y0 - 3 + 2 * (s + RING), b, full_bar(s + RING));
+      }
+    }
+  }
+  ptx::mbar_wait(wbar, 0);
+  __syncthreads();
+
+  // ---- tensor-core phase: each warp takes 4 channels ----
+  // Toeplitz B fragment of kernel row ky: B[k][n] = w[ky][k - n]; this lane holds k = 2t(+1), 2t+8(+9), n = g.
+  // Table word i of a kernel row = (w[i-1], w[i]) with w[-1] = w[7] = 0, word 8 = 0.
+  const int i0 = 2 * t - g + 1, i1 = i0 + 8;
+  const uint32_t o0 = static_cast<uint32_t>((i0 >= 0 && i0 <= 7) ? i0 : 8) * 4u;
+  const uint32_t o1 = static_cast<uint32_t>((i1 >= 0 && i1 <= 7) ? i1 : 8) * 4u;
+  // ldmatrix row address of this lane: tile j = lane >> 3 (kernel-row offset), row r = lane & 7
+  const int lj = lane >> 3, lr = lane & 7;
+  const uint32_t a_off = static_cast<uint32_t>(((lj & 1) * (IH / 2) + (lj >> 1) + lr) * G::ROW_B);
+
+
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    const int ch = warp * 4 + i;
+    const uint32_t plane = planes + ch * G::PLANE_B;
+    const uint32_t wrow = s_wtab + ch * (WTAB_WORDS * 4);
+    uint32_t b0[7], b1[7];
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+      b0[ky] = lds32(wrow + ky * 36 + o0);
+      b1[ky] = lds32(wrow + ky * 36 + o1);
+    }
+    const float bv = __ldg(bias + c0 + ch);
+    // A tiles T[j][xb]: rows {2r + j}, pixels 8xb .. 8xb+7
+    uint32_t T[8][NB + 1];
+#pragma unroll
+    for (int xb = 0; xb <= NB; ++xb) {
+      uint32_t lo[4], hi[4];
+      ldsm_x4(lo, plane + a_off + xb * 16);
+      ldsm_x4(hi, plane + a_off + 2 * G::ROW_B + xb * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { T[j][xb] = lo[j]; T[4 + j][xb] = hi[j]; }
+    }
+    float acc[NB][4];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nb][e] = bv;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+        mma_bf16_16816(acc[nb], T[ky][nb], T[ky + 1][nb], T[ky][nb + 1], T[ky + 1][nb + 1], b0[ky], b1[ky]);
+    // this warp is the only reader of plane `ch`: once its tiles are in registers the plane can take the
+    // outputs (rows 2g / 2g+1 of the mma tile, 18-word rows: conflict-free for this access pattern)
+    __syncwarp();
+    const uint32_t op = plane + (2 * g) * (OROW_W * 4) + t * 4;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      sts32(op + nb * 16, pack2(acc[nb][0], acc[nb][1]));
+      sts32(op + OROW_W * 4 + nb * 16, pack2(acc[nb][2], acc[nb][3]));
+    }
+  }
+  __syncthreads();
+
+  // ---- output planes -> NHWC staging tile ----
+  for (int task = warp; task < TH * NB; task += THREADS / 32) {
+    const int y = task / NB, xb = task % NB;
+    uint32_t R[4];
+    const uint32_t src = planes + g * G::PLANE_B + y * (OROW_W * 4) + (xb * 4 + t) * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) R[q] = lds32(src + q * 8 * G::PLANE_B);
+    const int px = y * G::TW + xb * 8 + (lane & 7);
+    const int cv = lane >> 3;
+    stsm_x4_trans(ring + px * 64 + ((cv ^ ((px >> 1) & 3)) << 4), R);
+  }
+  ptx::fence_proxy_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_4d(&tmap_out, c0, x0, y0, b, ring);
+    ptx::tma_store_commit();
+    ptx::tma_store_wait_read<0>();
+  }
+}
+
+// word i (0..8) of kernel row ky for channel c: (w[ky][i-1], w[ky][i]) as bf16, zero outside 0..6
+__global__ void dwconv7_wtab_kernel(const float* __restrict__ w, int C, uint32_t* __restrict__ wtab) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * WTAB_WORDS) return;
+  const int c = idx / WTAB_WORDS, j = idx % WTAB_WORDS;
+  uint32_t v = 0;
+  if (j < 63) {
+    const int ky = j / 9, i = j % 9;
+    const float lo = (i >= 1 && i <= 7) ? w[static_cast<size_t>(ky * 7 + i - 1) * C + c] : 0.0f;
+    const float hi = (i <= 6) ? w[static_cast<size_t>(ky * 7 + i) * C + c] : 0.0f;
+    v = pack2(lo, hi);
+  }
+  wtab[idx] = v;
+}
+
+int make_tmap_nhwc(CUtensorMap* out, const void* ptr, int B, int H, int W, int C, int box_w, int box_h) {
+  TmaEncodeTiledFn fn = tma_encode_fn();
+  FVLA_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  FVLA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "TMA base must be 16-byte aligned");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(CB), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (NHWC) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 1;
+  }
+  return 0;
+}
+
+template <int NB>
+int launch_mma(const void* in, const uint32_t* wtab, const float* bias, void* out, int B, int H, int W, int C,
+               cudaStream_t stream) {
+  using G = Geo<NB>;
+  auto kfn = dwconv7_mma_kernel<NB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_B));
+    attr_set = true;
+  }
+  CUtensorMap ti, to;
+  if (int rc = make_tmap_nhwc(&ti, in, B, H, W, C, G::IW, 2)) return rc;
+  if (int rc = make_tmap_nhwc(&to, out, B, H, W, C, G::TW, TH)) return rc;
+  const int tiles_x = W / G::TW, n_cblk = C / CB;
+  dim3 grid(static_cast<unsigned>(tiles_x * (H / TH) * n_cblk), static_cast<unsigned>(B));
+  kfn<<<grid, THREADS, G::SMEM_B, stream>>>(ti, to, wtab, bias, tiles_x, n_cblk);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+bool dwconv7_mma_supported(int dtype, int H, int W, int C, int mult, int k, int stride, int act) {
+  return dtype == DT_BF16 && k == 7 && stride == 1 && mult == 1 && act == ACT_NONE && C % CB == 0 && H % TH == 0 &&
+         (W % 32 == 0 || W == 16);
+}
+
+size_t dwconv7_wtab_bytes(int C) { return static_cast<size_t>(C) * WTAB_WORDS * 4; }
+
+int dwconv7_mma_prepare(const float* w_packed, int C, uint32_t* wtab, cudaStream_t stream) {
+  const int n = C * WTAB_WORDS;
+  dwconv7_wtab_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(w_packed, C, wtab);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dwconv7_mma(const void* in, const uint32_t* wtab, const float* bias, void* out, int B, int H, int W, int C,
+                cudaStream_t stream) {
+  if (W % 32 == 0) return launch_mma<4>(in, wtab, bias, out, B, H, W, C, stream);
+  return launch_mma<2>(in, wtab, bias, out, B, H, W, C, stream);
+}
+
+}  // namespace fvla

@@ -261,6 +261,14 @@ int Engine::make_dw(DwW* d, const std::vector<float>& w, const std::vector<float
   d->bias = upload_f32(bias);
   FVLA_REQUIRE(d->w != nullptr && d->bias != nullptr, "cudaMalloc failed for a depthwise conv");
   d->cin = cin; d->mult = mult; d->k = k; d->stride = stride; d->act = act;
+  if (cfg.dtype == FVLA_BF16 && k == 7 && stride == 1 && mult == 1 && act == ACT_NONE && cin % 32 == 0) {
+    void* p = nullptr;
+    FVLA_CUDA_CHECK(cudaMalloc(&p, dwconv7_wtab_bytes(cin)));
+    dev_allocs_.push_back(p);
+    weight_bytes += dwconv7_wtab_bytes(cin);
+    d->wtab = static_cast<uint32_t*>(p);
+    if (int rc = dwconv7_mma_prepare(d->w, cin, d->wtab, nullptr)) return rc;
+  }
   return 0;
 }
 
@@ -642,7 +650,7 @@ int Engine::run_dw(const DwW& w, const void* in, void* out, int B, int H, int W,
   const double fl = 2.0 * w.k * w.k * static_cast<double>(B) * Ho * Wo * w.cin * w.mult;
   flops += fl;
   prof_begin(s);
-  const int rc = dwconv(cfg.dtype, in, w.w, w.bias, out, B, H, W, w.cin, w.mult, w.k, w.stride, w.act, s);
+  const int rc = dwconv(cfg.dtype, in, w.w, w.bias, out, B, H, W, w.cin, w.mult, w.k, w.stride, w.act, s, w.wtab);
   if (profile_) {
     const double e = static_cast<double>(esz());
     const double by = e * (static_cast<double>(B) * H * W * w.cin + static_cast<double>(B) * Ho * Wo * w.cin * w.mult) +

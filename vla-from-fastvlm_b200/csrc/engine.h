@@ -25,6 +25,7 @@ struct GemmW {  // packed nn.Linear / 1x1 conv
 struct DwW {  // packed depthwise / grouped conv
   float* w = nullptr;     // [k*k][Cout] fp32
   float* bias = nullptr;  // [Cout] fp32
+  uint32_t* wtab = nullptr;  // Toeplitz B-fragment table of the tensor-core 7x7 path (bf16 mode)
   int cin = 0, mult = 1, k = 3, stride = 1, act = 0;
 };
 struct VisBlock {

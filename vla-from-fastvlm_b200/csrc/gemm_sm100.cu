@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "kernels.h"
+#include "tma_host.h"
 
 #include <mutex>
 
@@ -385,13 +386,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
 // ---- host side: tensor maps + launch --------------------------------------------------------
 
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+}  // namespace
 
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
+TmaEncodeTiledFn tma_encode_fn() {
+  static TmaEncodeTiledFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
     void* sym = nullptr;
@@ -399,16 +397,18 @@ EncodeTiledFn get_encode_fn() {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
             cudaSuccess &&
         qres == cudaDriverEntryPointSuccess) {
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
+      fn = reinterpret_cast<TmaEncodeTiledFn>(sym);
     }
   });
   return fn;
 }
 
+namespace {
+
 // 2-D bf16 tensor [rows, cols] with row pitch ld (elements); box = box_rows x 64 cols, 128B swizzle.
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld,
                    int box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
+  TmaEncodeTiledFn fn = tma_encode_fn();
   FVLA_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   FVLA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "TMA base must be 16-byte aligned");
   FVLA_REQUIRE((ld * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");

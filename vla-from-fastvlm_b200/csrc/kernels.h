@@ -53,8 +53,18 @@ int stem_conv3x3_s2(int dtype, const void* in, const float* w_packed, const floa
 int stem_im2col_bf16(const void* in, void* col, int B, int H, int W, cudaStream_t stream);
 // Depthwise / grouped k x k conv, groups = Cin, Cout = mult*Cin (mult 1 or 2), pad k/2,
 // + bias (+ GELU).  w_packed: [k*k][Cout] fp32.
+// `wtab` (optional): the tensor-core 7x7 path's Toeplitz table from dwconv7_mma_prepare(); built on the
+// fly when null.
 int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, void* out, int B,
-           int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream);
+           int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream,
+           const uint32_t* wtab = nullptr);
+
+// tensor-core depthwise 7x7 (bf16, stride 1, no activation, C%32==0, H%16==0, W%32==0 or W==16): dwconv_mma.cu
+bool dwconv7_mma_supported(int dtype, int H, int W, int C, int mult, int k, int stride, int act);
+size_t dwconv7_wtab_bytes(int C);
+int dwconv7_mma_prepare(const float* w_packed, int C, uint32_t* wtab, cudaStream_t stream);
+int dwconv7_mma(const void* in, const uint32_t* wtab, const float* bias, void* out, int B, int H, int W,
+                int C, cudaStream_t stream);
 
 // smem-tiled bf16 fast path (stride 1, mult 1, k in {3,7}, W%64==0, H%8==0, C%32==0); dwconv() uses it
 bool dwconv_tiled_supported(int dtype, int H, int W, int C, int mult, int k, int stride);
