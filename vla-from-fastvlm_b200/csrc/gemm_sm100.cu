@@ -33,17 +33,18 @@ constexpr int UMMA_K = 16;
 constexpr int EPI_WPQ = 4;                        // epilogue warps per TMEM lane quarter
 constexpr int EPI_THREADS = 4 * EPI_WPQ * 32;     // 512
 constexpr int GEMM_THREADS = 128 + EPI_THREADS;   // 640
-constexpr int STAGING_BYTES = BLOCK_M * 64 * 2;  // 128 rows x 64 bf16 output columns (per buffer)
-constexpr int SLAB_BYTES = 32 * 64 * 2;          // one lane quarter's 32-row slab
+constexpr int SLAB_BYTES = 32 * 64 * 2;          // one warp's 32-row x 64-column staging slab
+constexpr int STAGING_BYTES = 4 * EPI_WPQ * SLAB_BYTES;  // one private slab per epilogue warp (64 KB)
 
 template <int BLOCK_N> struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N >= 192) ? 4 : (BLOCK_N == 128 ? 5 : 6);
+  static constexpr int STAGES = (BLOCK_N == 256) ? 3 : (BLOCK_N == 192 ? 4 : (BLOCK_N == 128 ? 5 : 6));
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGING_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
 struct EpiParams {
@@ -119,7 +120,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t smem_a0 = smem_base;
   const uint32_t smem_b0 = smem_base + STAGES * Cfg::A_BYTES;
   const uint32_t smem_stage0 = smem_base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = smem_stage0 + 2 * STAGING_BYTES;
+  const uint32_t bar_base = smem_stage0 + STAGING_BYTES;
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -212,30 +213,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
-    // Each TMEM lane quarter (32 tile rows) is served by EPI_WPQ warps that share a private
-    // 32-row x 64-column staging slab (double buffered) and their own TMA stores; a quarter only
-    // synchronises with itself (128-thread named barriers), never CTA-wide.  Four warps per
-    // scheduler give the MUFU/LDTM/LDG latencies something to hide behind.
-    const int ew = warp_idx & 3;            // TMEM lane quarter this warp may read (warp_idx % 4)
-    const int cq = (warp_idx - 4) >> 2;     // which slice of each sub-tile's columns this warp owns
+    // A warp may only read its own TMEM lane quarter (warp_idx % 4), which is also the scheduler it issues
+    // on: the four warps of a quarter share an issue port.  Each warp therefore owns WHOLE 32-row x 64-column
+    // output sub-tiles (private 4 KB staging slab, private TMA store), the sub-tiles of a tile rotating over
+    // the four warps of the quarter.  No barrier joins the warps, so they drift apart and one warp's TMEM
+    // load / store-drain / residual latency is covered by the others' math (the earlier shared-slab version
+    // kept all four in lock step: the latencies of every phase added up, see profiles/r01_gemm_epilogue_ab.txt).
+    const int ew = warp_idx & 3;            // TMEM lane quarter
+    const int grp = (warp_idx - 4) >> 2;    // which of the quarter's four warps
     const int row = ew * 32 + lane;         // tile row == TMEM lane
-    const int tq = cq * 32 + lane;          // thread index within the quarter's group
-    constexpr int QT = EPI_WPQ * 32;        // threads per quarter group
-    const bool q_leader = (cq == 0 && lane == 0);
-    const uint32_t slab0 = smem_stage0 + static_cast<uint32_t>(ew) * (2 * SLAB_BYTES);
+    const uint32_t slab = smem_stage0 + static_cast<uint32_t>(warp_idx - 4) * SLAB_BYTES;
+    const uint32_t sbase = slab + lane * 128;  // this thread's row inside the slab
     int acc = 0;
     uint32_t acc_phase = 0;
-    int sbuf = 0;
+    uint32_t sub_counter = 0;
     const int n_out_total = SWIGLU ? p.N / 2 : p.N;
-    constexpr int CPW = ACC_PER_SUB / EPI_WPQ;  // accumulator columns per warp per sub-tile (16 or 32)
-    constexpr int NCH = CPW / 16;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * BLOCK_M;
       const int n0 = (tile % num_n) * BLOCK_N;
       const int m = m0 + row;
-      const bool row_ok = m < p.M;
       float rs = 1.0f;
-      if (p.row_scale != nullptr && row_ok) rs = __ldg(p.row_scale + m);
+      if (p.row_scale != nullptr && m < p.M) rs = __ldg(p.row_scale + m);
 
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
@@ -243,85 +241,80 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 
 #pragma unroll 1
-      for (int sub = 0; sub < NUM_SUB; ++sub) {
-        const int acc_col0 = sub * ACC_PER_SUB;                 // first accumulator column
+      for (int sub = 0; sub < NUM_SUB; ++sub, ++sub_counter) {
+        if ((sub_counter & 3u) != static_cast<uint32_t>(grp)) continue;
+        const int acc_col0 = sub * ACC_PER_SUB;                    // first accumulator column
         const int out_col0 = (SWIGLU ? (n0 / 2) : n0) + sub * 64;  // first output column
-        if (out_col0 >= n_out_total) break;                     // whole sub-tile out of range
-        const uint32_t slab = slab0 + static_cast<uint32_t>(sbuf) * SLAB_BYTES;
-
-        // residual sub-tile (32 rows x 128 B): coalesced 16-byte loads, issued before anything else
-        constexpr int RPT = 256 / QT;  // 16-byte residual chunks per thread
-        uint4 rr[RPT];
+        if (out_col0 >= n_out_total) continue;                     // whole sub-tile out of range
+        // the TMA store this warp issued from its slab last time must have finished reading it
+        if (lane == 0) ptx::tma_store_wait_read<0>();
+        __syncwarp();
         if (!SWIGLU && p.resid != nullptr) {
+          // residual sub-tile (32 rows x 128 B): coalesced 16-byte loads into the slab
+          uint4 rr[8];
 #pragma unroll
-          for (int i = 0; i < RPT; ++i) {
-            const int idx = i * QT + tq;
+          for (int i = 0; i < 8; ++i) {
+            const int idx = i * 32 + lane;
             const int rrow = idx >> 3, rchunk = idx & 7;
             const int gm = m0 + ew * 32 + rrow, gc = out_col0 + rchunk * 8;
             rr[i] = make_uint4(0u, 0u, 0u, 0u);
             if (gm < p.M && gc + 8 <= p.N)
               rr[i] = __ldg(reinterpret_cast<const uint4*>(p.resid + static_cast<size_t>(gm) * p.ldr + gc));
           }
-        }
-        // accumulators: issue the TMEM loads now, consume after the slab hand-shake
-        uint32_t r[NCH][16];
 #pragma unroll
-        for (int h = 0; h < NCH; ++h)
-          ptx::tmem_ld_32x16(tmem_acc + static_cast<uint32_t>(acc_col0 + cq * CPW + h * 16), r[h]);
-        // the TMA store issued from this slab two sub-tiles ago must have finished reading it
-        if (q_leader) ptx::tma_store_wait_read<1>();
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "n"(QT) : "memory");
-        if (!SWIGLU && p.resid != nullptr) {
-#pragma unroll
-          for (int i = 0; i < RPT; ++i) {
-            const int idx = i * QT + tq;
+          for (int i = 0; i < 8; ++i) {
+            const int idx = i * 32 + lane;
             const int rrow = idx >> 3, rchunk = idx & 7;
             const uint32_t dst = slab + rrow * 128 + ((rchunk ^ (rrow & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(rr[i].x), "r"(rr[i].y),
                          "r"(rr[i].z), "r"(rr[i].w)
                          : "memory");
           }
-          asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "n"(QT) : "memory");
+          __syncwarp();
         }
-        const uint32_t sbase = slab + lane * 128;  // this thread's row inside the slab
-        ptx::tmem_ld_wait();
 
 #pragma unroll
-        for (int h = 0; h < NCH; ++h) {
-          float v[16];
+        for (int hp = 0; hp < ACC_PER_SUB / 32; ++hp) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(acc_col0 + hp * 32), r);
+          ptx::tmem_ld_wait();
+          float v[32];
           if (p.row_scale != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[h][j]) * rs;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rs;
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[h][j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           }
           if constexpr (SWIGLU) {
-            // columns are (gate, up) pairs: 16 accumulators -> 8 outputs = one 16-byte chunk
-            uint32_t o[4];
+            // columns are (gate, up) pairs: 32 accumulators -> 16 outputs = two 16-byte chunks
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float a0 = silu_fast(v[4 * j]) * v[4 * j + 1];
-              const float a1 = silu_fast(v[4 * j + 2]) * v[4 * j + 3];
-              o[j] = pack_bf16(a0, a1);
+            for (int c = 0; c < 2; ++c) {
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float a0 = silu_fast(v[16 * c + 4 * j]) * v[16 * c + 4 * j + 1];
+                const float a1 = silu_fast(v[16 * c + 4 * j + 2]) * v[16 * c + 4 * j + 3];
+                o[j] = pack_bf16(a0, a1);
+              }
+              const int chunk = 2 * hp + c;
+              const uint32_t dst = sbase + ((chunk ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]),
+                           "r"(o[2]), "r"(o[3])
+                           : "memory");
             }
-            const int chunk = 2 * cq + h;
-            const uint32_t dst = sbase + ((chunk ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]),
-                         "r"(o[2]), "r"(o[3])
-                         : "memory");
           } else {
-            const int nb = n0 + acc_col0 + cq * CPW + h * 16;  // global column of v[0]
+            const int nb = n0 + acc_col0 + hp * 32;  // global column of v[0]
             if (p.bias != nullptr) {
-              if (nb + 16 <= p.N) {
+              if (nb + 32 <= p.N) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 8; ++j) {
                   const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j);
                   v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
                 }
               } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
+                for (int j = 0; j < 32; ++j)
                   if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
               }
             }
@@ -329,15 +322,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
               gelu_half_hybrid(v);
             } else if (p.act == ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] *= 0.5f;
+              for (int j = 0; j < 32; ++j) v[j] *= 0.5f;
               gelu_half_hybrid(v);
             } else if (p.act == ACT_SILU) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
             }
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int chunk = (cq * CPW + h * 16) / 8 + c;
+            for (int c = 0; c < 4; ++c) {
+              const int chunk = hp * 4 + c;
               const uint32_t dst = sbase + ((chunk ^ (lane & 7)) << 4);
               if (p.resid != nullptr) {  // residual already sits at this slot (own row: no cross-lane hazard)
                 uint32_t w0, w1, w2, w3;
@@ -361,19 +354,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
         ptx::fence_proxy_async_smem();
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "n"(QT) : "memory");
-        if (q_leader) {
+        __syncwarp();
+        if (lane == 0) {
           ptx::tma_store_2d(&tmap_d, out_col0, m0 + ew * 32, slab);
           ptx::tma_store_commit();
         }
-        sbuf ^= 1;
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
       ptx::tc_fence_before();
       ptx::mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (q_leader) ptx::tma_store_wait<0>();
+    if (lane == 0) ptx::tma_store_wait<0>();
   }
 
   ptx::tc_fence_before();
