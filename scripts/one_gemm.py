@@ -1,4 +1,4 @@
-"""Launch one GEMM shape a few times (ncu target)."""
+"""One bf16 GEMM launch (for ncu): python scripts/one_gemm.py M N K [gelu]"""
 import sys
 from pathlib import Path
 
@@ -7,12 +7,13 @@ import torch  # noqa: E402
 
 from vla_fastvlm import _native as N  # noqa: E402
 
-M, Nn, K, act = [int(v) for v in sys.argv[1:5]]
+M, Nn, K = (int(x) for x in sys.argv[1:4])
+act = 1 if len(sys.argv) > 4 and sys.argv[4] == "gelu" else 0
 a = torch.randn(M, K, device="cuda").bfloat16()
 w = (torch.randn(Nn, K, device="cuda") / K ** 0.5).bfloat16()
 bias = torch.randn(Nn, device="cuda")
 out = torch.empty(M, Nn, device="cuda", dtype=torch.bfloat16)
-for _ in range(4):
+for _ in range(3):
     N.op_gemm(a, w, bias=bias, act=act, out=out)
 torch.cuda.synchronize()
 print("ok", float(out.float().abs().mean()))

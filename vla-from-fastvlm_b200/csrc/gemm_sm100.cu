@@ -27,7 +27,8 @@ namespace fvla {
 
 namespace {
 
-constexpr int BLOCK_M = 128;
+constexpr int BLOCK_M = 128;   // rows per CTA
+constexpr int PAIR_M = 256;    // rows per CTA pair = UMMA M under cta_group::2
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WPQ = 4;                        // epilogue warps per TMEM lane quarter
@@ -37,10 +38,11 @@ constexpr int SLAB_BYTES = 32 * 64 * 2;          // one warp's 32-row x 64-colum
 constexpr int STAGING_BYTES = 4 * EPI_WPQ * SLAB_BYTES;  // one private slab per epilogue warp (64 KB)
 
 template <int BLOCK_N> struct GemmCfg {
+  static constexpr int HALF_N = BLOCK_N / 2;           // rows of the W tile each CTA of the pair stages
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 3 : (BLOCK_N == 192 ? 4 : (BLOCK_N == 128 ? 5 : 6));
+  static constexpr int B_BYTES = HALF_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // per CTA
+  static constexpr int STAGES = (BLOCK_N == 256) ? 5 : (BLOCK_N == 192 ? 5 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
@@ -104,7 +106,7 @@ __device__ __forceinline__ float silu_fast(float x) {
 }
 
 template <int BLOCK_N, bool SWIGLU>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_w,
                          const __grid_constant__ CUtensorMap tmap_d, const EpiParams p) {
@@ -131,7 +133,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  // A CTA pair (cluster of 2, one TPC) works on one 256 x BLOCK_N tile: CTA r stages rows [128r, 128r+128) of A
+  // and rows [r*BLOCK_N/2, (r+1)*BLOCK_N/2) of the W tile; the leader issues cta_group::2 MMAs that read both
+  // shared memories and write each CTA's 128 accumulator rows into that CTA's own TMEM.
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_m = (p.M + PAIR_M - 1) / PAIR_M;
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -143,53 +150,52 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(full_bar(s), 2);    // leader's copy is the live one: one arrive.expect_tx per CTA
+      ptx::mbar_init(empty_bar(s), 1);   // multicast tcgen05.commit from the leader
     }
     for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), EPI_THREADS);
+      ptx::mbar_init(tfull_bar(a), 1);                 // multicast tcgen05.commit from the leader
+      ptx::mbar_init(tempty_bar(a), 2 * 4 * EPI_WPQ);  // leader's copy: one arrive per epilogue warp of the pair
     }
     ptx::fence_barrier_init();
   }
   if (warp_idx == 2) {
-    ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc_pair(tmem_ptr_smem, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish_pair();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync_all();
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp_idx == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BLOCK_M;
-        const int n0 = (tile % num_n) * BLOCK_N;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / num_n) * PAIR_M + static_cast<int>(cta_rank) * BLOCK_M;
+        const int n0 = (tile % num_n) * BLOCK_N + static_cast<int>(cta_rank) * Cfg::HALF_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          ptx::tma_load_2d(smem_a0 + stage * Cfg::A_BYTES, &tmap_a, kb * BLOCK_K, m0,
-                           full_bar(stage));
-          ptx::tma_load_2d(smem_b0 + stage * Cfg::B_BYTES, &tmap_w, kb * BLOCK_K, n0,
-                           full_bar(stage));
+          const uint32_t full_leader = ptx::mapa_rank(full_bar(stage), 0);
+          ptx::mbar_arrive_expect_tx_cluster(full_leader, Cfg::STAGE_BYTES);
+          ptx::tma_load_2d_pair(smem_a0 + stage * Cfg::A_BYTES, &tmap_a, kb * BLOCK_K, m0, full_leader);
+          ptx::tma_load_2d_pair(smem_b0 + stage * Cfg::B_BYTES, &tmap_w, kb * BLOCK_K, n0, full_leader);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp_idx == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N);
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -201,11 +207,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 bf16 = 32 B inside the swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k),
-                           db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(2 * k),
+                                db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-          if (kb == num_kb - 1) ptx::umma_commit(tfull_bar(acc));
+          ptx::umma_commit_pair(empty_bar(stage), 3);  // frees this smem slot in both CTAs once the MMAs retire
+          if (kb == num_kb - 1) ptx::umma_commit_pair(tfull_bar(acc), 3);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -228,8 +234,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t acc_phase = 0;
     uint32_t sub_counter = 0;
     const int n_out_total = SWIGLU ? p.N / 2 : p.N;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * BLOCK_M;
+    const uint32_t tempty_leader0 = ptx::mapa_rank(tempty_bar(0), 0);
+    const uint32_t tempty_leader1 = ptx::mapa_rank(tempty_bar(1), 0);
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile / num_n) * PAIR_M + static_cast<int>(cta_rank) * BLOCK_M;
       const int n0 = (tile % num_n) * BLOCK_N;
       const int m = m0 + row;
       float rs = 1.0f;
@@ -362,17 +370,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
       ptx::tc_fence_before();
-      ptx::mbar_arrive(tempty_bar(acc));
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) ptx::tma_store_wait<0>();
   }
 
+  // neither CTA may exit (or free TMEM) while the peer can still signal its barriers or the leader's MMAs read
+  // its shared memory
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync_all();
   if (warp_idx == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -430,15 +441,16 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   }
   CUtensorMap ta, tw, td;
   if (int rc = make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, BLOCK_M)) return rc;
-  if (int rc = make_tmap_bf16(&tw, g.W, g.N, g.K, g.ldw, BLOCK_N)) return rc;
+  if (int rc = make_tmap_bf16(&tw, g.W, g.N, g.K, g.ldw, Cfg::HALF_N)) return rc;
   const int n_out = SWIGLU ? g.N / 2 : g.N;
   if (int rc = make_tmap_bf16(&td, g.D, g.M, n_out, g.ldd, 32)) return rc;  // per-quarter 32-row stores
   EpiParams ep;
   ep.M = g.M; ep.N = g.N; ep.K = g.K;
   ep.bias = g.bias; ep.row_scale = g.row_scale;
   ep.resid = static_cast<const __nv_bfloat16*>(g.resid); ep.ldr = g.ldr; ep.act = g.act;
-  const int tiles = ceil_div(g.M, BLOCK_M) * ceil_div(g.N, BLOCK_N);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int tiles = ceil_div(g.M, PAIR_M) * ceil_div(g.N, BLOCK_N);
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
   kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tw, td, ep);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
