@@ -456,19 +456,22 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   return 0;
 }
 
-// Pick the N tile that wastes the fewest tensor-core columns; prefer wide tiles on ties.
+// Pick the N tile with the least padded work per unit of measured tile efficiency: narrow tiles move more
+// operand bytes per flop through the same smem ring (BLOCK_N = 128 sustains ~0.78 of the 256-wide rate on a
+// long-K GEMM, 64 about half), so e.g. N = 896 runs faster as 4 x 256 (12 % padding) than as 7 x 128.
 int pick_block_n(int N, bool swiglu) {
   const int cands_plain[4] = {256, 192, 128, 64};
+  const double eff_plain[4] = {1.0, 0.96, 0.78, 0.5};
   const int cands_glu[2] = {256, 128};
+  const double eff_glu[2] = {1.0, 0.78};
   const int* cands = swiglu ? cands_glu : cands_plain;
+  const double* eff = swiglu ? eff_glu : eff_plain;
   const int nc = swiglu ? 2 : 4;
   int best = cands[0];
-  long long best_cost = -1;
+  double best_cost = -1.0;
   for (int i = 0; i < nc; ++i) {
     const int bn = cands[i];
-    const long long padded = static_cast<long long>(ceil_div(N, bn)) * bn;
-    // small penalty for narrow tiles (more epilogue/TMA overhead per flop)
-    const long long cost = padded * 16 + (256 - bn);
+    const double cost = static_cast<double>(ceil_div(N, bn)) * bn / eff[i];
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
