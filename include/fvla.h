@@ -176,6 +176,12 @@ int fvla_op_attention(int32_t dtype, int32_t impl, const void* q, const void* k,
                       int32_t causal, const float* rope_cos, const float* rope_sin, void* stream);
 int fvla_op_rmsnorm(int32_t dtype, const void* x, const float* weight, void* out, int32_t rows,
                     int32_t H, float eps, void* stream);
+/* FastViTHD ConvFFN tail fused on chip (bf16, C in {96,192}, hidden %128 == 0) [EXT convffn.fc1 -> GELU -> fc2,
+ * + layer-scaled residual]: out = resid + w2 . gelu(w1 . x + b1) + b2.  w1 [hidden,C] and b1 are passed
+ * PRE-HALVED (the epilogue evaluates gelu from x/2); w2 [C,hidden]; resid may alias out. */
+int fvla_op_ffn_fused(const void* x, const void* w1_half, const float* b1_half, const void* w2,
+                      const float* b2, const void* resid, void* out, int32_t M, int32_t C,
+                      int32_t hidden, void* stream);
 int fvla_op_convert(int32_t src_dtype, const void* src, int32_t dst_dtype, void* dst, int64_t n,
                     void* stream);
 

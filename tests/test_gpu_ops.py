@@ -141,6 +141,29 @@ def test_gemm_f32(native, M, N, K, epi):
     _close(out, ref.float(), F32_TOL, f"gemm f32 {M}x{N}x{K} {epi}")
 
 
+@pytest.mark.parametrize("M,C,hidden", [(256, 192, 768), (1000, 192, 768), (4096, 96, 384), (37, 96, 128),
+                                        (20000, 192, 256), (33000, 96, 384)])
+def test_ffn_fused(native, M, C, hidden):
+    """fc1 -> GELU -> fc2 -> +residual with the hidden tensor kept on chip vs the same math in fp64
+    (bf16 operands, hidden rounded to bf16 as the kernel stores it)."""
+    dev = _dev()
+    g = torch.Generator().manual_seed(M + C + hidden)
+    x = torch.randn(M, C, generator=g).to(dev).bfloat16()
+    w1 = (torch.randn(hidden, C, generator=g) / math.sqrt(C)).to(dev).bfloat16()
+    b1 = (0.5 * torch.randn(hidden, generator=g)).to(dev)
+    w2 = (torch.randn(C, hidden, generator=g) / math.sqrt(hidden)).to(dev).bfloat16()
+    b2 = torch.randn(C, generator=g).to(dev)
+    resid = torch.randn(M, C, generator=g).to(dev).bfloat16()
+    out = native.op_ffn_fused(x, w1, b1, w2, b2, resid)
+    h = F.gelu(x.double() @ w1.double().t() + b1.double()).bfloat16().double()
+    ref = (h @ w2.double().t() + b2.double() + resid.double()).float()
+    _close(out, ref, BF16_TOL, f"ffn_fused M={M} C={C} hidden={hidden}")
+    # in place on the residual buffer (how the engine calls it)
+    buf = resid.clone()
+    native.op_ffn_fused(x, w1, b1, w2, b2, buf, out=buf)
+    assert torch.equal(buf, out), "in-place residual differs"
+
+
 def _pack_dw(w):  # [Cout,1,k,k] -> [k*k][Cout]
     cout, _, k, _ = w.shape
     return w.reshape(cout, k * k).t().contiguous()

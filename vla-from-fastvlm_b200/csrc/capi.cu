@@ -195,6 +195,15 @@ int fvla_op_rmsnorm(int32_t dtype, const void* x, const float* weight, void* out
   return fvla::rmsnorm(dtype, x, weight, out, rows, H, eps, static_cast<cudaStream_t>(stream));
 }
 
+int fvla_op_ffn_fused(const void* x, const void* w1_half, const float* b1_half, const void* w2,
+                      const float* b2, const void* resid, void* out, int32_t M, int32_t C, int32_t hidden,
+                      void* stream) {
+  fvla::FfnFusedArgs a;
+  a.x = x; a.w1 = w1_half; a.b1 = b1_half; a.w2 = w2; a.b2 = b2; a.resid = resid; a.out = out;
+  a.M = M; a.C = C; a.hidden = hidden;
+  return fvla::ffn_fused(a, static_cast<cudaStream_t>(stream));
+}
+
 int fvla_op_convert(int32_t src_dtype, const void* src, int32_t dst_dtype, void* dst, int64_t n,
                     void* stream) {
   return fvla::convert(src_dtype, src, dst_dtype, dst, n, static_cast<cudaStream_t>(stream));

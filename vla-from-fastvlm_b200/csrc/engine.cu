@@ -1,6 +1,8 @@
 // Engine: weight import (HF state-dict names), BatchNorm / layer-scale folding, repacking, workspace
 // and the launch sequence of the FastVLA forward.  See engine.h / include/fvla.h.
 #include "engine.h"
+
+#include <cstdlib>
 #include "common.cuh"
 
 #include <algorithm>
@@ -644,6 +646,29 @@ int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, con
   return rc;
 }
 
+// ConvFFN tail: out = resid + fc2(gelu(fc1(z))).  Fused on chip where the kernel covers the width (stages 0/1 in
+// bf16), otherwise two GEMMs through the 4x hidden buffer `hid`.
+int Engine::run_ffn(const VisBlock& blk, const void* z, void* hid, void* out_resid, int M, cudaStream_t s) {
+  const int d = blk.fc1.K, hd = blk.fc1.N;
+  static const bool fuse_ffn = std::getenv("FVLA_DISABLE_FUSED_FFN") == nullptr;  // A/B switch for profiling
+  if (fuse_ffn && blk.fc1.half_in && blk.fc1.bias != nullptr && blk.fc2.bias != nullptr &&
+      ffn_fused_supported(cfg.dtype, d, hd)) {
+    FfnFusedArgs a;
+    a.x = z; a.w1 = blk.fc1.w; a.b1 = blk.fc1.bias; a.w2 = blk.fc2.w; a.b2 = blk.fc2.bias;
+    a.resid = out_resid; a.out = out_resid; a.M = M; a.C = d; a.hidden = hd;
+    ++launches;
+    const double fl = 4.0 * M * static_cast<double>(hd) * d;
+    flops += fl;
+    prof_begin(s);
+    const int rc = ffn_fused(a, s);
+    prof_end("vis.ffn_fused M" + std::to_string(M) + " C" + std::to_string(d) + " H" + std::to_string(hd), fl,
+             static_cast<double>(esz()) * (3.0 * M * d + 2.0 * hd * d), s);
+    return rc;
+  }
+  if (int rc = run_gemm(blk.fc1, z, hid, M, ACT_GELU, nullptr, false, s)) return rc;
+  return run_gemm(blk.fc2, hid, out_resid, M, ACT_NONE, out_resid, false, s);
+}
+
 int Engine::run_dw(const DwW& w, const void* in, void* out, int B, int H, int W, cudaStream_t s) {
   ++launches;
   const int Ho = (H - 1) / w.stride + 1, Wo = (W - 1) / w.stride + 1;
@@ -804,8 +829,7 @@ int Engine::vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats
         // RepMixerBlock: x = mixer(x); x = x + ls * ConvFFN(x)
         if (int rc = run_dw(blk.mixer, X, Y, bc, side, side, s)) return rc;
         if (int rc = run_dw(blk.ffn_dw, Y, Z, bc, side, side, s)) return rc;
-        if (int rc = run_gemm(blk.fc1, Z, Hb, M, ACT_GELU, nullptr, false, s)) return rc;
-        if (int rc = run_gemm(blk.fc2, Hb, Y, M, ACT_NONE, Y, false, s)) return rc;
+        if (int rc = run_ffn(blk, Z, Hb, Y, M, s)) return rc;
         std::swap(X, Y);
       } else {
         // AttentionBlock: x = x + ls1 * MHSA(BN(x)); x = x + ls2 * ConvFFN(x)
@@ -825,8 +849,7 @@ int Engine::vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats
                  4.0 * bc * static_cast<double>(at.N) * at.N * d, 4.0 * M * static_cast<double>(d) * e, s);
         if (int rc = run_gemm(blk.proj, Z, X, M, ACT_NONE, X, false, s)) return rc;
         if (int rc = run_dw(blk.ffn_dw, X, Z, bc, side, side, s)) return rc;
-        if (int rc = run_gemm(blk.fc1, Z, Hb, M, ACT_GELU, nullptr, false, s)) return rc;
-        if (int rc = run_gemm(blk.fc2, Hb, X, M, ACT_NONE, X, false, s)) return rc;
+        if (int rc = run_ffn(blk, Z, Hb, X, M, s)) return rc;
       }
     }
     if (int rc = tap(FVLA_TAP_VIS_STAGE0 + i, X, static_cast<size_t>(M) * d * e,

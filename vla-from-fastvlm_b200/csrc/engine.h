@@ -95,6 +95,7 @@ class Engine {
 
   int run_gemm(const GemmW& w, const void* A, void* D, int M, int act, const void* resid, bool swiglu,
                cudaStream_t s);
+  int run_ffn(const VisBlock& blk, const void* z, void* hid, void* out_resid, int M, cudaStream_t s);
   int run_dw(const DwW& w, const void* in, void* out, int B, int H, int W, cudaStream_t s);
   int vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats, cudaStream_t s);
 

@@ -20,6 +20,7 @@
 #include "ptx_sm100.cuh"
 #include "kernels.h"
 #include "tma_host.h"
+#include "epilogue_math.cuh"
 
 #include <mutex>
 
@@ -58,52 +59,7 @@ struct EpiParams {
   int act;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-// ---- epilogue activations -----------------------------------------------------------------------
-// The XU (MUFU) pipe is the scarce resource of the small-K GEMM epilogues: ncu shows it 100 % busy at
-// ~4 tanh/clk/SM (profiles/r01_gemm_gelu_k192_ncu.txt), i.e. 8192 cycles for a 128x256 tile whose MMAs
-// take 1536-3072.  ex2+rcp is no better (two MUFU ops).  GELU is therefore evaluated two ways and the
-// elements of a thread are split between them so that the XU and FMA pipes finish together:
-//   3 of 8 elements:  h + h*tanh(h*Q(h^2))          1 MUFU + 7 FP32 slots   (|err| <= 2.5e-5 + 2^-11 rel)
-//   5 of 8 elements:  h + h*th*R(th^2), th=clamp(h) 0 MUFU + 11 FP32 slots  (|err| <= 1.9e-4)
-// both in terms of h = x/2 (GELU GEMMs are packed with weights/bias pre-halved, exact in bf16), both
-// approximations of the erf form nn.GELU() computes.  The fp32 parity mode keeps erff.
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// Phi(x) = (1 + tanh(P(x)))/2 with P fitted to atanh(erf(x/sqrt2)); h^2 clamped where tanh has saturated
-__device__ __forceinline__ float gelu_half_mufu(float h) {
-  const float u = fminf(h * h, 16.0f);
-  const float q = fmaf(u, fmaf(u, -1.124853725e-02f, 2.96045168e-01f), 1.594015768f);
-  return fmaf(h, tanh_approx(h * q), h);
-}
-// erf(x/sqrt2) ~= x*R(x^2) on |x| <= 4 (odd minimax polynomial, 7 coefficients), +-1 outside
-__device__ __forceinline__ float gelu_half_poly(float h) {
-  const float th = fminf(fmaxf(h, -2.0f), 2.0f);
-  const float s = th * th;
-  float r = fmaf(s, 3.732471752e-04f, -6.547819094e-03f);
-  r = fmaf(s, r, 4.910614436e-02f);
-  r = fmaf(s, r, -2.083871470e-01f);
-  r = fmaf(s, r, 5.614317921e-01f);
-  r = fmaf(s, r, -1.033169161e+00f);
-  r = fmaf(s, r, 1.591533285e+00f);
-  return fmaf(h, th * r, h);
-}
-template <int N>
-__device__ __forceinline__ void gelu_half_hybrid(float (&v)[N]) {
-#pragma unroll
-  for (int j = 0; j < N; ++j) v[j] = ((j & 7) % 3 == 0) ? gelu_half_mufu(v[j]) : gelu_half_poly(v[j]);
-}
-// x * sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU (SwiGLU has one per TWO accumulators)
-__device__ __forceinline__ float silu_fast(float x) {
-  const float h = 0.5f * x;
-  return fmaf(h, tanh_approx(h), h);
-}
+using namespace epi;
 
 template <int BLOCK_N, bool SWIGLU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -408,6 +364,8 @@ TmaEncodeTiledFn tma_encode_fn() {
 
 namespace {
 
+}  // namespace
+
 // 2-D bf16 tensor [rows, cols] with row pitch ld (elements); box = box_rows x 64 cols, 128B swizzle.
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld,
                    int box_rows) {
@@ -428,6 +386,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, long long 
   }
   return 0;
 }
+
+namespace {
 
 template <int BLOCK_N, bool SWIGLU>
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {

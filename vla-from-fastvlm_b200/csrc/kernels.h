@@ -30,6 +30,22 @@ inline int gemm(int dtype, const GemmArgs& g, cudaStream_t s) {
   return dtype == DT_BF16 ? gemm_bf16(g, s) : gemm_f32(g, s);
 }
 
+// ---- fused ConvFFN tail (bf16, C in {96, 192}): out = resid + W2 . gelu(W1 . x + b1) + b2 ------------------
+// W1/b1 are stored PRE-HALVED (the GELU epilogue takes x/2, like ACT_GELU_HALF); the 4x hidden tensor stays on
+// chip (ffn_fused_sm100.cu).
+struct FfnFusedArgs {
+  const void* x = nullptr;      // [M, C]
+  const void* w1 = nullptr;     // [hidden, C]  (x 1/2)
+  const float* b1 = nullptr;    // [hidden]     (x 1/2)
+  const void* w2 = nullptr;     // [C, hidden]
+  const float* b2 = nullptr;    // [C]
+  const void* resid = nullptr;  // [M, C], may alias out
+  void* out = nullptr;          // [M, C]
+  int M = 0, C = 0, hidden = 0;
+};
+bool ffn_fused_supported(int dtype, int C, int hidden);
+int ffn_fused(const FfnFusedArgs& a, cudaStream_t stream);
+
 // ---- image ingest ----------------------------------------------------------------------------
 struct PreprocessArgs {
   const void* src = nullptr; int src_dtype = DT_F32;  // DT_F32 / DT_U8 / DT_BF16

@@ -11,4 +11,7 @@ using TmaEncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint3
                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 TmaEncodeTiledFn tma_encode_fn();  // null when the driver does not export it
 
+// 2-D bf16 tensor [rows, cols], row pitch ld (elements); box = box_rows x 64 columns, SWIZZLE_128B, zero OOB fill
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
+
 }  // namespace fvla

@@ -122,6 +122,7 @@ _SIGNATURES = {
     "fvla_op_attention": (C.c_int, [_I32, _I32, _VP, _VP, _VP, _I32, _VP, _I32, _I32, _I32, _I32, _I32,
                                     _I32, _F32, _I32, _VP, _VP, _VP]),
     "fvla_op_rmsnorm": (C.c_int, [_I32, _VP, _VP, _VP, _I32, _I32, _F32, _VP]),
+    "fvla_op_ffn_fused": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP]),
     "fvla_op_convert": (C.c_int, [_I32, _VP, _I32, _VP, _I64, _VP]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -251,6 +252,24 @@ def op_stem_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor) ->
     out = torch.empty((B, H // 2, W // 2, cout), device=x.device, dtype=x.dtype)
     check(load().fvla_op_stem_conv(dtype_code(x.dtype), ptr(x), ptr(w_packed), ptr(bias), ptr(out), B, H,
                                    W, cout, stream_ptr()), "fvla_op_stem_conv")
+    return out
+
+
+def op_ffn_fused(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+                 resid: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = resid + w2 . gelu(w1 . x + b1) + b2 (bf16).  Takes the un-halved fc1 parameters and halves them
+    here, the way the engine packs them at finalize (x/2 is exact in bf16)."""
+    M, Cc = x.shape
+    hidden = w1.shape[0]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and resid.is_contiguous()
+    w1h = (w1.float() * 0.5).to(torch.bfloat16).contiguous()
+    b1h = (b1.float() * 0.5).contiguous()
+    w2c = w2.to(torch.bfloat16).contiguous()
+    b2c = b2.float().contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(load().fvla_op_ffn_fused(ptr(x), ptr(w1h), ptr(b1h), ptr(w2c), ptr(b2c), ptr(resid), ptr(out), M, Cc,
+                                   hidden, stream_ptr()), "fvla_op_ffn_fused")
     return out
 
 
