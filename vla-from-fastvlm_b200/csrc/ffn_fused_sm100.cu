@@ -165,7 +165,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && cta_rank == 0) {
+    // The whole warp runs the control flow (barrier waits, stage arithmetic) so that descriptors and addresses
+    // stay in uniform registers; only the tcgen05 instructions themselves sit under elect_one.  With a single
+    // divergent thread every UTCHMMA cost ~15 dependent instructions of operand marshalling, comparable to
+    // the 64 cycles an M=256, N=128 instruction executes for.
+    if (cta_rank == 0) {
       constexpr uint32_t idesc1 = ptx::make_idesc_bf16(FPAIR_M, HC);
       constexpr uint32_t idesc2 = ptx::make_idesc_bf16(FPAIR_M, C);
       int stage = 0;
@@ -188,16 +192,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               const uint64_t db = ptx::make_kmajor_sw128_desc(smem_w + stage * Cfg::STAGE_BYTES);
               constexpr int NK_FULL = 4;
               const int nk = (C - kp * 64) / 16 < NK_FULL ? (C - kp * 64) / 16 : NK_FULL;
+              if (ptx::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < NK_FULL; ++k)
-                if (k < nk)
-                  ptx::umma_bf16_pair(tmem_s, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                                      idesc1, (kp | k) != 0 ? 1u : 0u);
-              ptx::umma_commit_pair(wempty(stage), 3);
+                for (int k = 0; k < NK_FULL; ++k)
+                  if (k < nk)
+                    ptx::umma_bf16_pair(tmem_s, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                                        idesc1, (kp | k) != 0 ? 1u : 0u);
+                ptx::umma_commit_pair(wempty(stage), 3);
+                if (kp == Cfg::KP - 1) {
+                  ptx::umma_commit_pair(sfull(b), 3);
+                  if (j == nch - 1) ptx::umma_commit_pair(xempty, 3);  // X may be refilled for the next tile
+                }
+              }
+              __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
-            ptx::umma_commit_pair(sfull(b), 3);
-            if (j == nch - 1) ptx::umma_commit_pair(xempty, 3);  // X may be refilled for the next tile
             ++g1;
           }
           if (j >= 1) {
@@ -215,18 +224,22 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               ptx::tc_fence_after();
               const uint64_t da = ptx::make_kmajor_sw128_desc(smem_h + b * Cfg::H_BYTES + kb * PANEL_BYTES);
               const uint64_t db = ptx::make_kmajor_sw128_desc(smem_w + stage * Cfg::STAGE_BYTES);
+              if (ptx::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                ptx::umma_bf16_pair(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                                    idesc2, (j > 1 || kb != 0 || k != 0) ? 1u : 0u);
-              ptx::umma_commit_pair(wempty(stage), 3);
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_bf16_pair(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                                      idesc2, (j > 1 || kb != 0 || k != 0) ? 1u : 0u);
+                ptx::umma_commit_pair(wempty(stage), 3);
+                if (kb == HC / 64 - 1) ptx::umma_commit_pair(hempty(b), 3);
+              }
+              __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
-            ptx::umma_commit_pair(hempty(b), 3);
             ++g2;
           }
         }
-        ptx::umma_commit_pair(ofull, 3);
+        if (ptx::elect_one()) ptx::umma_commit_pair(ofull, 3);
+        __syncwarp();
       }
     }
   } else if (warp_idx >= 4) {

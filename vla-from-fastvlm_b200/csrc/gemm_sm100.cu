@@ -145,7 +145,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && cta_rank == 0) {
+    // warp-uniform control flow, tcgen05 instructions under elect_one: descriptors stay in uniform registers and
+    // the four UTCHMMAs of a k-block issue back to back
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -160,14 +162,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           ptx::tc_fence_after();
           const uint64_t da = ptx::make_kmajor_sw128_desc(smem_a0 + stage * Cfg::A_BYTES);
           const uint64_t db = ptx::make_kmajor_sw128_desc(smem_b0 + stage * Cfg::B_BYTES);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B inside the swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(2 * k),
-                                db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 B inside the swizzle row: +2 in the (addr >> 4) field
+              ptx::umma_bf16_pair(tmem_d, da + static_cast<uint64_t>(2 * k),
+                                  db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit_pair(empty_bar(stage), 3);  // frees this smem slot in both CTAs once the MMAs retire
+            if (kb == num_kb - 1) ptx::umma_commit_pair(tfull_bar(acc), 3);
           }
-          ptx::umma_commit_pair(empty_bar(stage), 3);  // frees this smem slot in both CTAs once the MMAs retire
-          if (kb == num_kb - 1) ptx::umma_commit_pair(tfull_bar(acc), 3);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
