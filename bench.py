@@ -277,7 +277,8 @@ def main() -> None:
             tot = sum(r["total_ms"] for r in rows)
             fam = {}
             for r in rows:
-                key = ("gemm_tcgen05" if "gemm" in r["label"] else "dwconv" if "dwconv" in r["label"] else
+                key = ("gemm_tcgen05" if ("gemm" in r["label"] or "ffn_fused" in r["label"]) else
+                       "dwconv" if "dwconv" in r["label"] else
                        "attention" if "attention" in r["label"] else "other")
                 f = fam.setdefault(key, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
                 f["ms"] += r["total_ms"]; f["flops"] += r["flops"]; f["bytes"] += r["bytes"]; f["launches"] += r["count"]
@@ -289,9 +290,19 @@ def main() -> None:
             peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
             gm = fam.get("gemm_tcgen05", dict(ms=1.0, flops=0.0, launches=1))
             achieved = gm["flops"] / gm["ms"] / 1e9
-            roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of a step)",
+            # DRAM bytes per launch of the same kernels from the committed ncu pass (profiles/, same command line);
+            # null until that file exists
+            traffic = None
+            tj = ROOT / "profiles" / "r01_ncu_traffic.json"
+            if tj.is_file():
+                tr = json.loads(tj.read_text()).get("tcgen05_gemm_family", {})
+                if tr.get("launches"):
+                    traffic = tr["dram_bytes"] / tr["launches"]
+            roof = {"bound": "tensor",
+                    "kernel": "gemm_bf16_tcgen05_kernel + ffn_fused_kernel (all tcgen05 launches of a step)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "algorithmic_bytes_per_launch": gm["bytes"] / max(1, gm["launches"]),
+                    "peak_source": peak_src,
                     "avg_launch_ms": gm["ms"] / max(1, gm["launches"]), "share_of_step": gm["ms"] / tot}
             hbm = float(peaks.get("hbm_gbs", 6650.0))
             breakdown = {k: {"ms_per_step": v["ms"] / n_prof, "share": v["ms"] / tot,
