@@ -1,4 +1,4 @@
-"""Launch one depthwise-conv shape a few times (ncu target)."""
+"""One depthwise-conv launch (for ncu): python scripts/one_dwconv.py B HW C k stride mult"""
 import sys
 from pathlib import Path
 
@@ -7,11 +7,11 @@ import torch  # noqa: E402
 
 from vla_fastvlm import _native as N  # noqa: E402
 
-B, HW, C, k = [int(v) for v in sys.argv[1:5]]
+B, HW, C, k, stride, mult = (int(x) for x in sys.argv[1:7])
 x = torch.randn(B, HW, HW, C, device="cuda").bfloat16()
-w = torch.randn(k * k, C, device="cuda")
-b = torch.randn(C, device="cuda")
-for _ in range(4):
-    out = N.op_dwconv(x, w, b, k, 1, 1, 0)
+w = torch.randn(k * k, C * mult, device="cuda") / k
+b = torch.randn(C * mult, device="cuda")
+for _ in range(3):
+    out = N.op_dwconv(x, w, b, k, stride, mult, 0)
 torch.cuda.synchronize()
 print("ok", float(out.float().abs().mean()))

@@ -55,12 +55,12 @@ template <int NB> struct Geo {
   static constexpr int PLANE_W = PLANE_IN_W > OPLANE_W ? PLANE_IN_W : OPLANE_W;
   static constexpr int PLANE_B = PLANE_W * 4;
   static constexpr int SLAB_B = 2 * IW * 64;
-  static constexpr int OUT_B = TH * TW * 64;
-  static constexpr int RING_B = (RING * SLAB_B > OUT_B) ? RING * SLAB_B : OUT_B;
+  static constexpr int RING_B = (RING * SLAB_B + 1023) / 1024 * 1024;
   static constexpr int PLANES_B = CB * PLANE_B;
   static constexpr int WTAB_B = CB * WTAB_WORDS * 4;
+  static constexpr int WSTAGE_B = (THREADS / 32) * 1024;
   static constexpr int BAR_B = 128;
-  static constexpr int SMEM_B = RING_B + PLANES_B + WTAB_B + BAR_B + 1024;
+  static constexpr int SMEM_B = RING_B + PLANES_B + WTAB_B + WSTAGE_B + BAR_B + 1024;
   static_assert((ROW_B / 16) % 2 == 1, "plane rows must be an odd number of 16-byte units");
   static_assert(SLAB_B % 512 == 0, "slabs must keep the 64-byte swizzle phase");
   static_assert(PLANE_W % 8 == 4, "plane pitch must be 4 (mod 8) words");
@@ -125,75 +125,60 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 // {2r + j} an A-fragment tile needs are consecutive (conflict-free ldmatrix) for either parity of j
 __device__ __forceinline__ int plane_row(int y) { return (y & 1) * (IH / 2) + (y >> 1); }
 
+struct TileCoord { int c0, x0, y0, b; };
+
+template <int NB>
+__device__ __forceinline__ TileCoord decode_tile(int id, int n_cblk, int tiles_x, int tiles_y) {
+  TileCoord tc;
+  tc.c0 = (id % n_cblk) * CB;  // channel blocks of one spatial tile are neighbours in time: they share L2 lines
+  id /= n_cblk;
+  tc.x0 = (id % tiles_x) * Geo<NB>::TW;
+  id /= tiles_x;
+  tc.y0 = (id % tiles_y) * TH;
+  tc.b = id / tiles_y;
+  return tc;
+}
+
+// Persistent: a CTA walks tiles id = blockIdx.x, += gridDim.x.  The TMA loads of the NEXT tile's first RING
+// slabs are issued as soon as this tile's slabs have been transposed into the planes, so they are in flight
+// while the tensor-core and store phases of this tile run (ncu of the one-tile-per-CTA version: 25 % of all
+// warp samples sat in the slab-arrival wait, ~20 KB in flight per SM against the ~65 KB HBM needs).
 template <int NB>
 __global__ void __launch_bounds__(THREADS, 2)
-dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
-                   const uint32_t* __restrict__ wtab, const float* __restrict__ bias, int tiles_x, int n_cblk) {
+dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* __restrict__ wtab,
+                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int C,
+                   int tiles_x, int tiles_y, int n_cblk, int total_tiles) {
   using G = Geo<NB>;
   extern __shared__ uint8_t smem_dwm[];
   const uint32_t base = (ptx::smem_u32(smem_dwm) + 1023u) & ~1023u;
   const uint32_t ring = base;
   const uint32_t planes = ring + G::RING_B;
   const uint32_t s_wtab = planes + G::PLANES_B;
-  const uint32_t bars = s_wtab + G::WTAB_B;
+  const uint32_t wstage = s_wtab + G::WTAB_B;   // per-warp 2 x 512 B transposition buffers of the writer
+  const uint32_t bars = wstage + G::WSTAGE_B;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   const uint32_t wbar = bars + 8u * NSLAB;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int cblk = blockIdx.x % n_cblk;
-  const int tile = blockIdx.x / n_cblk;
-  const int x0 = (tile % tiles_x) * G::TW, y0 = (tile / tiles_x) * TH;
-  const int c0 = cblk * CB;
-  const int b = blockIdx.y;
 
   if (tid == 0) {
     ptx::prefetch_tmap(&tmap_in);
-    ptx::prefetch_tmap(&tmap_out);
     for (int s = 0; s <= NSLAB; ++s) ptx::mbar_init(bars + 8u * s, 1);
     ptx::fence_barrier_init();
   }
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && static_cast<int>(blockIdx.x) < total_tiles) {
+    const TileCoord tc = decode_tile<NB>(blockIdx.x, n_cblk, tiles_x, tiles_y);
     ptx::mbar_arrive_expect_tx(wbar, G::WTAB_B);
-    bulk_g2s(s_wtab, wtab + static_cast<size_t>(c0) * WTAB_WORDS, G::WTAB_B, wbar);
+    bulk_g2s(s_wtab, wtab + static_cast<size_t>(tc.c0) * WTAB_WORDS, G::WTAB_B, wbar);
 #pragma unroll
     for (int s = 0; s < RING; ++s) {
       ptx::mbar_arrive_expect_tx(full_bar(s), G::SLAB_B);
-      tma_load_4d(ring + s * G::SLAB_B, &tmap_in, c0, x0 - 3, y0 - 3 + 2 * s, b, full_bar(s));
+      tma_load_4d(ring + s * G::SLAB_B, &tmap_in, tc.c0, tc.x0 - 3, tc.y0 - 3 + 2 * s, tc.b, full_bar(s));
     }
   }
 
-  // ---- NHWC slabs -> per-channel planes ----
-  for (int s = warp; s < NSLAB; s += THREADS / 32) {
-    const int buf = s % RING;
-    ptx::mbar_wait(full_bar(s), 0);
-    const uint32_t slab = ring + buf * G::SLAB_B;
-#pragma unroll
-    for (int task = 0; task < 2 * G::XB; ++task) {
-      const int r = task / G::XB, xb = task % G::XB;
-      const int px = r * G::IW + xb * 8 + (lane & 7);
-      const int cv = lane >> 3;
-      uint32_t R[4];
-      ldsm_x4_trans(R, slab + px * 64 + ((cv ^ ((px >> 1) & 3)) << 4));
-      const int y = 2 * s + r;
-      const uint32_t dst = planes + g * G::PLANE_B + plane_row(y) * G::ROW_B + (xb * 4 + t) * 4;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) sts32(dst + q * 8 * G::PLANE_B, R[q]);
-    }
-    if (s + RING < NSLAB) {
-      __syncwarp();
-      if (lane == 0) {
-        ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive_expect_tx(full_bar(s + RING), G::SLAB_B);
-        tma_load_4d(slab, &tmap_in, c0, x0 - 3, y0 - 3 + 2 * (s + RING), b, full_bar(s + RING));
-      }
-    }
-  }
-  ptx::mbar_wait(wbar, 0);
-  __syncthreads();
-
-  // ---- tensor-core phase: each warp takes 4 channels ----
   // Toeplitz B fragment of kernel row ky: B[k][n] = w[ky][k - n]; this lane holds k = 2t(+1), 2t+8(+9), n = g.
   // Table word i of a kernel row = (w[i-1], w[i]) with w[-1] = w[7] = 0, word 8 = 0.
   const int i0 = 2 * t - g + 1, i1 = i0 + 8;
@@ -203,68 +188,125 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   const int lj = lane >> 3, lr = lane & 7;
   const uint32_t a_off = static_cast<uint32_t>(((lj & 1) * (IH / 2) + (lj >> 1) + lr) * G::ROW_B);
 
+  uint32_t parity = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, parity ^= 1u) {
+    const TileCoord tc = decode_tile<NB>(tile, n_cblk, tiles_x, tiles_y);
+    const int next = tile + static_cast<int>(gridDim.x);
 
+    // ---- NHWC slabs -> per-channel planes ----
+    for (int s = warp; s < NSLAB; s += THREADS / 32) {
+      const int buf = s % RING;
+      ptx::mbar_wait(full_bar(s), parity);
+      const uint32_t slab = ring + buf * G::SLAB_B;
+#pragma unroll
+      for (int task = 0; task < 2 * G::XB; ++task) {
+        const int r = task / G::XB, xb = task % G::XB;
+        const int px = r * G::IW + xb * 8 + (lane & 7);
+        const int cv = lane >> 3;
+        uint32_t R[4];
+        ldsm_x4_trans(R, slab + px * 64 + ((cv ^ ((px >> 1) & 3)) << 4));
+        const int y = 2 * s + r;
+        const uint32_t dst = planes + g * G::PLANE_B + plane_row(y) * G::ROW_B + (xb * 4 + t) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sts32(dst + q * 8 * G::PLANE_B, R[q]);
+      }
+      if (s + RING < NSLAB) {
+        __syncwarp();
+        if (lane == 0) {
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive_expect_tx(full_bar(s + RING), G::SLAB_B);
+          tma_load_4d(slab, &tmap_in, tc.c0, tc.x0 - 3, tc.y0 - 3 + 2 * (s + RING), tc.b, full_bar(s + RING));
+        }
+      }
+    }
+    ptx::mbar_wait(wbar, parity);
+    __syncthreads();  // planes complete, every slab of this tile consumed: the ring is free
+    if (tid == 0 && next < total_tiles) {
+      const TileCoord nt = decode_tile<NB>(next, n_cblk, tiles_x, tiles_y);
+      ptx::fence_proxy_async_smem();
+#pragma unroll
+      for (int s = 0; s < RING; ++s) {
+        ptx::mbar_arrive_expect_tx(full_bar(s), G::SLAB_B);
+        tma_load_4d(ring + s * G::SLAB_B, &tmap_in, nt.c0, nt.x0 - 3, nt.y0 - 3 + 2 * s, nt.b, full_bar(s));
+      }
+    }
+
+    // ---- tensor-core phase: each warp takes 4 channels ----
 #pragma unroll 1
-  for (int i = 0; i < 4; ++i) {
-    const int ch = warp * 4 + i;
-    const uint32_t plane = planes + ch * G::PLANE_B;
-    const uint32_t wrow = s_wtab + ch * (WTAB_WORDS * 4);
-    uint32_t b0[7], b1[7];
+    for (int i = 0; i < 4; ++i) {
+      const int ch = warp * 4 + i;
+      const uint32_t plane = planes + ch * G::PLANE_B;
+      const uint32_t wrow = s_wtab + ch * (WTAB_WORDS * 4);
+      uint32_t b0[7], b1[7];
 #pragma unroll
-    for (int ky = 0; ky < 7; ++ky) {
-      b0[ky] = lds32(wrow + ky * 36 + o0);
-      b1[ky] = lds32(wrow + ky * 36 + o1);
-    }
-    const float bv = __ldg(bias + c0 + ch);
-    // A tiles T[j][xb]: rows {2r + j}, pixels 8xb .. 8xb+7
-    uint32_t T[8][NB + 1];
+      for (int ky = 0; ky < 7; ++ky) {
+        b0[ky] = lds32(wrow + ky * 36 + o0);
+        b1[ky] = lds32(wrow + ky * 36 + o1);
+      }
+      const float bv = __ldg(bias + tc.c0 + ch);
+      // A tiles T[j][xb]: rows {2r + j}, pixels 8xb .. 8xb+7
+      uint32_t T[8][NB + 1];
 #pragma unroll
-    for (int xb = 0; xb <= NB; ++xb) {
-      uint32_t lo[4], hi[4];
-      ldsm_x4(lo, plane + a_off + xb * 16);
-      ldsm_x4(hi, plane + a_off + 2 * G::ROW_B + xb * 16);
+      for (int xb = 0; xb <= NB; ++xb) {
+        uint32_t lo[4], hi[4];
+        ldsm_x4(lo, plane + a_off + xb * 16);
+        ldsm_x4(hi, plane + a_off + 2 * G::ROW_B + xb * 16);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { T[j][xb] = lo[j]; T[4 + j][xb] = hi[j]; }
-    }
-    float acc[NB][4];
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[nb][e] = bv;
-#pragma unroll
-    for (int ky = 0; ky < 7; ++ky)
+        for (int j = 0; j < 4; ++j) { T[j][xb] = lo[j]; T[4 + j][xb] = hi[j]; }
+      }
+      float acc[NB][4];
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb)
-        mma_bf16_16816(acc[nb], T[ky][nb], T[ky + 1][nb], T[ky][nb + 1], T[ky + 1][nb + 1], b0[ky], b1[ky]);
-    // this warp is the only reader of plane `ch`: once its tiles are in registers the plane can take the
-    // outputs (rows 2g / 2g+1 of the mma tile, 18-word rows: conflict-free for this access pattern)
-    __syncwarp();
-    const uint32_t op = plane + (2 * g) * (OROW_W * 4) + t * 4;
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      sts32(op + nb * 16, pack2(acc[nb][0], acc[nb][1]));
-      sts32(op + OROW_W * 4 + nb * 16, pack2(acc[nb][2], acc[nb][3]));
+        for (int e = 0; e < 4; ++e) acc[nb][e] = bv;
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+          mma_bf16_16816(acc[nb], T[ky][nb], T[ky + 1][nb], T[ky][nb + 1], T[ky + 1][nb + 1], b0[ky], b1[ky]);
+      // this warp is the only reader of plane `ch`: once its tiles are in registers the plane can take the
+      // outputs (rows 2g / 2g+1 of the mma tile, 18-word rows: conflict-free for this access pattern)
+      __syncwarp();
+      const uint32_t op = plane + (2 * g) * (OROW_W * 4) + t * 4;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        sts32(op + nb * 16, pack2(acc[nb][0], acc[nb][1]));
+        sts32(op + OROW_W * 4 + nb * 16, pack2(acc[nb][2], acc[nb][3]));
+      }
     }
-  }
-  __syncthreads();
+    __syncthreads();  // output planes complete; the Toeplitz table is no longer read
+    if (tid == 0 && next < total_tiles) {
+      const TileCoord nt = decode_tile<NB>(next, n_cblk, tiles_x, tiles_y);
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive_expect_tx(wbar, G::WTAB_B);
+      bulk_g2s(s_wtab, wtab + static_cast<size_t>(nt.c0) * WTAB_WORDS, G::WTAB_B, wbar);
+    }
 
-  // ---- output planes -> NHWC staging tile ----
-  for (int task = warp; task < TH * NB; task += THREADS / 32) {
-    const int y = task / NB, xb = task % NB;
-    uint32_t R[4];
-    const uint32_t src = planes + g * G::PLANE_B + y * (OROW_W * 4) + (xb * 4 + t) * 4;
+    // ---- output planes -> NHWC: 8 px x 32 ch blocks through a per-warp 512-byte buffer, 64-byte runs to HBM ----
+    {
+      const uint32_t mine = wstage + static_cast<uint32_t>(warp) * 1024u;
+      const int spx = lane >> 2, schunk = lane & 3;  // this lane's 16 bytes of the transposed block
+      int k = 0;
+      for (int task = warp; task < TH * NB; task += THREADS / 32, ++k) {
+        const int y = task / NB, xb = task % NB;
+        uint32_t R[4];
+        const uint32_t src = planes + g * G::PLANE_B + y * (OROW_W * 4) + (xb * 4 + t) * 4;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) R[q] = lds32(src + q * 8 * G::PLANE_B);
-    const int px = y * G::TW + xb * 8 + (lane & 7);
-    const int cv = lane >> 3;
-    stsm_x4_trans(ring + px * 64 + ((cv ^ ((px >> 1) & 3)) << 4), R);
-  }
-  ptx::fence_proxy_async_smem();
-  __syncthreads();
-  if (tid == 0) {
-    tma_store_4d(&tmap_out, c0, x0, y0, b, ring);
-    ptx::tma_store_commit();
-    ptx::tma_store_wait_read<0>();
+        for (int q = 0; q < 4; ++q) R[q] = lds32(src + q * 8 * G::PLANE_B);
+        const uint32_t buf = mine + static_cast<uint32_t>(k & 1) * 512u;
+        const int px = lane & 7, cv = lane >> 3;
+        stsm_x4_trans(buf + px * 64 + ((cv ^ ((px >> 1) & 3)) << 4), R);
+        __syncwarp();
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(buf + spx * 64 + ((schunk ^ ((spx >> 1) & 3)) << 4)));
+        __nv_bfloat16* dst = out + ((static_cast<size_t>(tc.b) * H + tc.y0 + y) * W + tc.x0 + xb * 8 + spx) * C +
+                             tc.c0 + schunk * 8;
+        *reinterpret_cast<uint4*>(dst) = v;
+      }
+    }
+    __syncthreads();  // the planes are rewritten by the next tile's transposition
   }
 }
 
@@ -313,12 +355,15 @@ int launch_mma(const void* in, const uint32_t* wtab, const float* bias, void* ou
     FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_B));
     attr_set = true;
   }
-  CUtensorMap ti, to;
+  CUtensorMap ti;
   if (int rc = make_tmap_nhwc(&ti, in, B, H, W, C, G::IW, 2)) return rc;
-  if (int rc = make_tmap_nhwc(&to, out, B, H, W, C, G::TW, TH)) return rc;
-  const int tiles_x = W / G::TW, n_cblk = C / CB;
-  dim3 grid(static_cast<unsigned>(tiles_x * (H / TH) * n_cblk), static_cast<unsigned>(B));
-  kfn<<<grid, THREADS, G::SMEM_B, stream>>>(ti, to, wtab, bias, tiles_x, n_cblk);
+  const int tiles_x = W / G::TW, tiles_y = H / TH, n_cblk = C / CB;
+  const long long total = static_cast<long long>(tiles_x) * tiles_y * n_cblk * B;
+  FVLA_REQUIRE(total < (1ll << 31), "dwconv7_mma: too many tiles");
+  const int resident = 2 * num_sms();  // two CTAs per SM (shared memory), each walking a stride of tiles
+  const int grid = total < resident ? static_cast<int>(total) : resident;
+  kfn<<<grid, THREADS, G::SMEM_B, stream>>>(ti, wtab, bias, static_cast<__nv_bfloat16*>(out), H, W, C, tiles_x,
+                                           tiles_y, n_cblk, static_cast<int>(total));
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
