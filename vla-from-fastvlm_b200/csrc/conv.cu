@@ -478,6 +478,8 @@ int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, 
     }
     return dwconv7_mma(in, wtab, bias, out, B, H, W, Cin, stream);
   }
+  if (dwconv_s2m2_tiled_supported(dtype, H, W, Cin, mult, ksize, stride) && (act == ACT_NONE || act == ACT_GELU))
+    return dwconv_s2m2_tiled(in, w_packed, bias, out, B, H, W, Cin, act, stream);
   if (dwconv_tiled_supported(dtype, H, W, Cin, mult, ksize, stride))
     return dwconv_tiled(in, w_packed, bias, out, B, H, W, Cin, ksize, act, stream);
   if (dtype == DT_F32)

@@ -211,11 +211,171 @@ int launch_tiled_h(const void* in, const float* w, const float* bias, void* out,
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stride-2, x2-channel grouped 7x7 (FastViTHD patch-embed `proj.0`: groups = Cin, Cout = 2 Cin) + bias + GELU.
+// Same scheme as above — halo tile staged once as fp16, packed-half taps flushed into fp32 every two kernel
+// rows — with two twists: output pixel o reads inputs 2o + kx (a lane's 4 outputs slide over 13 inputs per
+// kernel row), and output channels (2c, 2c+1) both read input channel c, so each loaded value is duplicated
+// into both halves of a register and ONE HFMA2 serves the channel pair.
+// CTA = 8 output rows x 32 output pixels x 32 output channels; tile [21 rows][4 vecs of 4 in-ch][69 px] fp16.
+// ---------------------------------------------------------------------------------------------
+constexpr int S2_TWO = 32, S2_THO = 8, S2_CBO = 32;
+constexpr int S2_IW = 2 * S2_TWO + 5, S2_IH = 2 * S2_THO + 5;
+constexpr int S2_XP_RAW = S2_IW + (S2_IW >> 3) + 1;
+constexpr int S2_XP = S2_XP_RAW + ((4 - (S2_XP_RAW & 15)) & 15);  // = 4 (mod 16) 8-byte slots: conflict-free LDS.64
+constexpr int S2_IN_BYTES = S2_IH * 4 * S2_XP * 8;
+constexpr int S2_SMEM = S2_IN_BYTES + 49 * (S2_CBO / 2) * 4;
+
+__device__ __forceinline__ uint32_t dup_lo(uint32_t v) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %1, 0x1010;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ uint32_t dup_hi(uint32_t v) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %1, 0x3232;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+__global__ void __launch_bounds__(256, 2)
+dwconv7_s2m2_tiled_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W,
+                          int Cin, int act) {
+  constexpr int K = 7;
+  extern __shared__ __align__(16) uint8_t smem_dw2[];
+  const uint32_t s_in = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dw2));
+  uint32_t* s_wh = reinterpret_cast<uint32_t*>(smem_dw2 + S2_IN_BYTES);  // [49][16] half2 = out-channel pairs
+  const int Ho = H / 2, Wo = W / 2, Cout = 2 * Cin;
+  const int tiles_x = Wo / S2_TWO;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int co0 = blockIdx.y * S2_CBO, ci0 = co0 / 2;
+  const int b = blockIdx.z;
+  const int xo0 = tx * S2_TWO, yo0 = ty * S2_THO;
+  const int tid = threadIdx.x;
+
+  // ---- stage the halo tile: 16 input channels per pixel = two 16-byte loads, bf16 -> fp16 ----
+  const __nv_bfloat16* img = in + static_cast<size_t>(b) * H * W * Cin + ci0;
+  constexpr int NV = S2_IH * S2_IW * 2;
+  for (int idx = tid; idx < NV; idx += 256) {
+    const int hv = idx & 1;  // which 8 of the 16 input channels
+    const int xi = (idx >> 1) % S2_IW;
+    const int r = (idx >> 1) / S2_IW;
+    const int gy = 2 * yo0 + r - 3, gx = 2 * xo0 + xi - 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = __ldg(reinterpret_cast<const uint4*>(img + (static_cast<size_t>(gy) * W + gx) * Cin + hv * 8));
+    const uint32_t slot = static_cast<uint32_t>(xi + (xi >> 3)) * 8u;
+    const uint32_t d0 = s_in + static_cast<uint32_t>((r * 4 + 2 * hv) * S2_XP) * 8u + slot;
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d0), "r"(bf16x2_to_f16x2_sat(v.x)),
+                 "r"(bf16x2_to_f16x2_sat(v.y))
+                 : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d0 + S2_XP * 8u), "r"(bf16x2_to_f16x2_sat(v.z)),
+                 "r"(bf16x2_to_f16x2_sat(v.w))
+                 : "memory");
+  }
+  for (int idx = tid; idx < K * K * (S2_CBO / 2); idx += 256) {
+    const int t = idx / (S2_CBO / 2), cp = idx % (S2_CBO / 2);
+    const float w0 = __ldg(w + static_cast<size_t>(t) * Cout + co0 + 2 * cp);
+    const float w1 = __ldg(w + static_cast<size_t>(t) * Cout + co0 + 2 * cp + 1);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(w1), "f"(w0));
+    s_wh[idx] = r;
+  }
+  __syncthreads();
+
+  // ---- compute: warp = output row, lane = (vector of 4 input = 8 output channels, group of 4 output px) ----
+  const int row = tid >> 5, lane = tid & 31;
+  const int cv = lane & 3, pg = lane >> 2;
+  float acc[4][8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + co0 + cv * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + co0 + cv * 8) + 1);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
+      acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+    }
+  }
+  uint32_t racc[4][4];
+#pragma unroll 1
+  for (int ky = 0; ky < K; ++ky) {
+    uint32_t wr[K][4];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const uint4 wv = *reinterpret_cast<const uint4*>(s_wh + (ky * K + kx) * (S2_CBO / 2) + cv * 4);
+      wr[kx][0] = wv.x; wr[kx][1] = wv.y; wr[kx][2] = wv.z; wr[kx][3] = wv.w;
+    }
+    const bool fresh = (ky & 1) == 0;
+    const uint32_t line = s_in + static_cast<uint32_t>(((2 * row + ky) * 4 + cv) * S2_XP) * 8u;
+#pragma unroll
+    for (int i = 0; i < 2 * 3 + K; ++i) {  // inputs 2o + kx, o < 4, kx < 7
+      const int xi = pg * 8 + i;
+      uint32_t a, bb;
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(bb) : "r"(line + static_cast<uint32_t>(xi + (xi >> 3)) * 8u));
+      const uint32_t x[4] = {dup_lo(a), dup_hi(a), dup_lo(bb), dup_hi(bb)};
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int kx = i - 2 * o;
+        if (kx < 0 || kx >= K) continue;
+        if (kx == 0 && fresh) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) racc[o][c] = hmul2_u(x[c], wr[0][c]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) racc[o][c] = hfma2_u(x[c], wr[kx][c], racc[o][c]);
+        }
+      }
+    }
+    if (!fresh || ky == K - 1) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float2 f = h2_to_f2(racc[o][c]);
+          acc[o][2 * c] += f.x;
+          acc[o][2 * c + 1] += f.y;
+        }
+    }
+  }
+  __nv_bfloat16* orow =
+      out + ((static_cast<size_t>(b) * Ho + (yo0 + row)) * Wo + xo0 + pg * 4) * Cout + co0 + cv * 8;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    Vec8<__nv_bfloat16> r;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) r.v[c] = acc[o][c];
+    if (act == ACT_GELU) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) r.v[c] = gelu_tanh_fit(r.v[c]);
+    }
+    r.store(orow + static_cast<size_t>(o) * Cout);
+  }
+}
+
 }  // namespace
 
 bool dwconv_tiled_supported(int dtype, int H, int W, int C, int mult, int k, int stride) {
   return dtype == DT_BF16 && stride == 1 && mult == 1 && (k == 3 || k == 7) && W % TW == 0 &&
          H % TH == 0 && C % CB == 0;
+}
+
+bool dwconv_s2m2_tiled_supported(int dtype, int H, int W, int Cin, int mult, int k, int stride) {
+  return dtype == DT_BF16 && stride == 2 && mult == 2 && k == 7 && H % 2 == 0 && W % 2 == 0 &&
+         (W / 2) % S2_TWO == 0 && (H / 2) % S2_THO == 0 && (2 * Cin) % S2_CBO == 0;
+}
+
+int dwconv_s2m2_tiled(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int Cin,
+                      int act, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FVLA_CUDA_CHECK(cudaFuncSetAttribute(dwconv7_s2m2_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((W / 2 / S2_TWO) * (H / 2 / S2_THO), 2 * Cin / S2_CBO, B);
+  dwconv7_s2m2_tiled_kernel<<<grid, 256, S2_SMEM, stream>>>(static_cast<const __nv_bfloat16*>(in), w, bias,
+                                                             static_cast<__nv_bfloat16*>(out), H, W, Cin, act);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }
 
 int dwconv_tiled(const void* in, const float* w, const float* bias, void* out, int B, int H, int W,

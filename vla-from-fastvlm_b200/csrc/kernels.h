@@ -75,6 +75,11 @@ int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, 
            int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream,
            const uint32_t* wtab = nullptr);
 
+// smem-tiled stride-2 x2-channel grouped 7x7 (patch-embed proj.0), bf16, Wo%32==0, Ho%8==0, Cout%32==0
+bool dwconv_s2m2_tiled_supported(int dtype, int H, int W, int Cin, int mult, int k, int stride);
+int dwconv_s2m2_tiled(const void* in, const float* w_packed, const float* bias, void* out, int B, int H, int W,
+                      int Cin, int act, cudaStream_t stream);
+
 // tensor-core depthwise 7x7 (bf16, stride 1, no activation, C%32==0, H%16==0, W%32==0 or W==16): dwconv_mma.cu
 bool dwconv7_mma_supported(int dtype, int H, int W, int C, int mult, int k, int stride, int act);
 size_t dwconv7_wtab_bytes(int C);
