@@ -340,10 +340,10 @@ def test_rmsnorm(native, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_se_gelu(native, dtype):
+@pytest.mark.parametrize("B,HW,Cc,Cr", [(3, 256, 512, 32), (2, 256, 3072, 192), (9, 64, 104, 8)])
+def test_se_gelu(native, dtype, B, HW, Cc, Cr):
     dev = _dev()
     g = torch.Generator().manual_seed(21)
-    B, HW, Cc, Cr = 3, 256, 512, 32
     x = torch.randn(B, HW, Cc, generator=g).to(dev).to(dtype)
     w1 = (torch.randn(Cr, Cc, generator=g) / math.sqrt(Cc)).to(dev)
     b1 = torch.randn(Cr, generator=g).to(dev)

@@ -339,30 +339,53 @@ se_mean_kernel(const T* __restrict__ x, float* __restrict__ mean, int HW, int C)
   }
 }
 
-// one block per sample: hidden = relu(W1 mean + b1) [Cr]; gate = sigmoid(W2 hidden + b2) [C]
-__global__ void se_fc_kernel(const float* __restrict__ mean, const float* __restrict__ w1,
-                             const float* __restrict__ b1, const float* __restrict__ w2,
-                             const float* __restrict__ b2, float* __restrict__ gate, int C, int Cr) {
-  extern __shared__ float sh[];  // [C] mean, [Cr] hidden
-  float* smean = sh;
-  float* shid = sh + C;
-  const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) smean[i] = mean[static_cast<size_t>(b) * C + i];
-  __syncthreads();
+// hidden[b][r] = relu(W1[r] . mean[b] + b1[r]): one block per reduced channel r, the 3072-wide weight row held in
+// registers, warps striding over the samples (coalesced reads on both operands).  The previous one-block-per-sample
+// kernel streamed both weight matrices (4.7 MB) through every block with a stride-Cr access on W2: 0.53 ms at any
+// batch size, 8 % of the b=1 forward.
+__global__ void __launch_bounds__(256)
+se_fc1_kernel(const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ b1,
+              float* __restrict__ hidden, int B, int C, int Cr) {
+  constexpr int MAXV = 16;  // C <= 32 * MAXV * ... handled by the strided loop below
+  const int r = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int r = warp; r < Cr; r += nw) {
-    const float* wr = w1 + static_cast<size_t>(r) * C;
+  const float* wr = w1 + static_cast<size_t>(r) * C;
+  float wreg[MAXV * 8];
+  const int nv = (C + 31) / 32;  // elements per lane (<= 128)
+#pragma unroll
+  for (int i = 0; i < MAXV * 8; ++i) wreg[i] = (i < nv && lane + 32 * i < C) ? __ldg(wr + lane + 32 * i) : 0.f;
+  const float bias = b1[r];
+  for (int b = warp; b < B; b += nw) {
+    const float* m = mean + static_cast<size_t>(b) * C;
     float a = 0.f;
-    for (int i = lane; i < C; i += 32) a = fmaf(wr[i], smean[i], a);
+#pragma unroll
+    for (int i = 0; i < MAXV * 8; ++i)
+      if (i < nv && lane + 32 * i < C) a = fmaf(wreg[i], m[lane + 32 * i], a);
     a = warp_sum(a);
-    if (lane == 0) shid[r] = fmaxf(a + b1[r], 0.f);
+    if (lane == 0) hidden[static_cast<size_t>(b) * Cr + r] = fmaxf(a + bias, 0.f);
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float* wr = w2 + static_cast<size_t>(c) * Cr;
-    float a = b2[c];
-    for (int i = 0; i < Cr; ++i) a = fmaf(wr[i], shid[i], a);
-    gate[static_cast<size_t>(b) * C + c] = 1.f / (1.f + expf(-a));
+}
+// gate[b][c] = sigmoid(W2[c] . hidden[b] + b2[c]): one warp per output channel, weight row in registers
+__global__ void __launch_bounds__(256)
+se_fc2_kernel(const float* __restrict__ hidden, const float* __restrict__ w2, const float* __restrict__ b2,
+              float* __restrict__ gate, int B, int C, int Cr) {
+  constexpr int MAXV = 8;  // Cr <= 256
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (c >= C) return;
+  const float* wr = w2 + static_cast<size_t>(c) * Cr;
+  float wreg[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) wreg[i] = (lane + 32 * i < Cr) ? __ldg(wr + lane + 32 * i) : 0.f;
+  const float bias = b2[c];
+  for (int b = 0; b < B; ++b) {
+    const float* h = hidden + static_cast<size_t>(b) * Cr;
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (lane + 32 * i < Cr) a = fmaf(wreg[i], h[lane + 32 * i], a);
+    a = warp_sum(a);
+    if (lane == 0) gate[static_cast<size_t>(b) * C + c] = 1.f / (1.f + expf(-(a + bias)));
   }
 }
 
@@ -387,10 +410,16 @@ int se_gelu_t(const void* x, void* out, int B, int HW, int C, int Cr, const floa
               cudaStream_t s) {
   dim3 g1(ceil_div(C, 64), B);
   se_mean_kernel<T><<<g1, 256, 0, s>>>(static_cast<const T*>(x), mean, HW, C);
-  se_fc_kernel<<<B, 256, (C + Cr) * sizeof(float), s>>>(mean, w1, b1, w2, b2, gate, C, Cr);
+  // no extra scratch: fc1 writes the hidden vectors [B, Cr] into the gate buffer, fc2 reads them from there and
+  // writes the gates [B, C] over the (now consumed) means, which the scale kernel then reads
+  FVLA_REQUIRE(C <= 4096 && Cr <= 256 && Cr <= C, "se_gelu: channel counts out of range");
+  float* hidden = gate;
+  float* gates = mean;
+  se_fc1_kernel<<<Cr, 256, 0, s>>>(mean, w1, b1, hidden, B, C, Cr);
+  se_fc2_kernel<<<ceil_div(C, 8), 256, 0, s>>>(hidden, w2, b2, gates, B, C, Cr);
   const long long tv = static_cast<long long>(B) * HW * (C / 8);
   se_scale_gelu_kernel<T><<<static_cast<unsigned>(ceil_div_ll(tv, 256)), 256, 0, s>>>(
-      static_cast<const T*>(x), gate, static_cast<T*>(out), HW, C, tv);
+      static_cast<const T*>(x), gates, static_cast<T*>(out), HW, C, tv);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
