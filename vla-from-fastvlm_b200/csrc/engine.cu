@@ -2,6 +2,8 @@
 // and the launch sequence of the FastVLA forward.  See engine.h / include/fvla.h.
 #include "engine.h"
 
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 #include "common.cuh"
 
@@ -348,7 +350,19 @@ int Engine::pack_vision() {
       for (int k = 0; k < hd; ++k) w2[static_cast<size_t>(n) * hd + k] = f2w->data[static_cast<size_t>(n) * hd + k] * l;
       b2[n] = f2b->data[n] * l;
     }
-    return make_gemm(&blk->fc2, w2, d, hd, &b2);
+    if (int rc = make_gemm(&blk->fc2, w2, d, hd, &b2)) return rc;
+    if (ffn_fused_supported(cfg.dtype, d, hd)) {
+      // the fused ConvFFN kernel keeps its hidden tensor in fp16 and runs fc2 as an fp16 x fp16 MMA
+      std::vector<__half> h(w2.size());
+      for (size_t i = 0; i < w2.size(); ++i) h[i] = __float2half_rn(w2[i]);
+      void* p = nullptr;
+      FVLA_CUDA_CHECK(cudaMalloc(&p, h.size() * 2));
+      FVLA_CUDA_CHECK(cudaMemcpy(p, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+      dev_allocs_.push_back(p);
+      weight_bytes += h.size() * 2;
+      blk->fc2.w_f16 = p;
+    }
+    return 0;
   };
 
   stages_.clear();
@@ -651,10 +665,10 @@ int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, con
 int Engine::run_ffn(const VisBlock& blk, const void* z, void* hid, void* out_resid, int M, cudaStream_t s) {
   const int d = blk.fc1.K, hd = blk.fc1.N;
   static const bool fuse_ffn = std::getenv("FVLA_DISABLE_FUSED_FFN") == nullptr;  // A/B switch for profiling
-  if (fuse_ffn && blk.fc1.half_in && blk.fc1.bias != nullptr && blk.fc2.bias != nullptr &&
+  if (fuse_ffn && blk.fc1.half_in && blk.fc1.bias != nullptr && blk.fc2.bias != nullptr && blk.fc2.w_f16 != nullptr &&
       ffn_fused_supported(cfg.dtype, d, hd)) {
     FfnFusedArgs a;
-    a.x = z; a.w1 = blk.fc1.w; a.b1 = blk.fc1.bias; a.w2 = blk.fc2.w; a.b2 = blk.fc2.bias;
+    a.x = z; a.w1 = blk.fc1.w; a.b1 = blk.fc1.bias; a.w2 = blk.fc2.w_f16; a.b2 = blk.fc2.bias;
     a.resid = out_resid; a.out = out_resid; a.M = M; a.C = d; a.hidden = hd;
     ++launches;
     const double fl = 4.0 * M * static_cast<double>(hd) * d;

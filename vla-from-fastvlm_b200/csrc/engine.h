@@ -18,6 +18,7 @@ struct HostTensor {
 
 struct GemmW {  // packed nn.Linear / 1x1 conv
   void* w = nullptr;          // [N, K] in engine dtype
+  void* w_f16 = nullptr;      // same matrix as fp16, only for fc2 of blocks served by the fused ConvFFN kernel
   const float* bias = nullptr;  // [N] fp32 or null
   int N = 0, K = 0;
   bool half_in = false;       // weights+bias pre-scaled by 1/2: the GELU epilogue takes x/2 (ACT_GELU_HALF)

@@ -89,5 +89,33 @@ __device__ __forceinline__ float silu_fast(float x) {
 }
 
 
+// ---- GELU on packed half pairs, for hidden tensors that are stored as fp16 ---------------------------------------
+// Where the consumer of a GELU output is another tensor-core GEMM of ours, the hidden tensor can be fp16 instead of
+// bf16 (3 more mantissa bits; ConvFFN activations are O(1..100), far inside fp16 range; the consuming weights are
+// converted to fp16 at pack time).  The whole activation then runs two elements per instruction:
+//   h2 = cvt.f16x2(x0/2, x1/2);  u = min(h2*h2, 16);  q = c0 + u*(c1 + u*c2);  t = tanh.approx.f16x2(h2*q);
+//   out = h2 + h2*t                                   -- 8 issue slots and ONE MUFU op per PAIR (fp32 form: 26 / 2)
+// Same tanh-form fit as gelu_half_mufu2; tanh.approx.f16x2 carries ~2^-11 absolute error, the same order as the
+// fp32 tanh.approx it replaces, and the fp16 result is stored without a second rounding.
+__device__ __forceinline__ uint32_t h2_splat(float c) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %1;" : "=r"(r) : "f"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t gelu_half_f16x2(float h_lo, float h_hi) {
+  uint32_t h, u, q, a, t, o;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(h_hi), "f"(h_lo));
+  const uint32_t c0 = h2_splat(1.594015768f), c1 = h2_splat(2.96045168e-01f), c2 = h2_splat(-1.124853725e-02f);
+  const uint32_t k16 = h2_splat(16.0f);
+  asm("mul.rn.f16x2 %0, %1, %1;" : "=r"(u) : "r"(h));
+  asm("min.f16x2 %0, %1, %2;" : "=r"(u) : "r"(u), "r"(k16));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(q) : "r"(u), "r"(c2), "r"(c1));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(q) : "r"(u), "r"(q), "r"(c0));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(a) : "r"(h), "r"(q));
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(a));
+  asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(o) : "r"(h), "r"(t));
+  return o;
+}
+
 }  // namespace epi
 }  // namespace fvla

@@ -9,13 +9,13 @@
 //     X tile [128 x C] resident in shared memory (one TMA load per tile)
 //     for each 128-wide hidden chunk j:
 //       GEMM1  S[j&1] (TMEM, 128 x 128 fp32)  = X . W1[j]^T          W1 panels streamed through a TMA ring
-//       epilogue warps: S -> +b1 -> GELU -> bf16 -> H[j&1] in shared memory, written directly in the
+//       epilogue warps: S -> +b1 -> GELU (packed-half, epilogue_math.cuh) -> fp16 H[j&1] in shared memory, in the
 //                       K-major SWIZZLE_128B layout the tensor core reads its A operand from
-//       GEMM2  O (TMEM, 128 x C fp32)        += H[j&1] . W2[:, j]^T   W2 panels through the same ring
+//       GEMM2  O (TMEM, 128 x C fp32)        += H[j&1] . W2[:, j]^T   fp16 x fp16; W2 (fp16) through the same ring
 //     epilogue warps: O -> +b2 -> +resid -> bf16 -> staging slab -> TMA store
 //
-// GEMM1 of chunk j+1 is issued before GEMM2 of chunk j, so the tensor core works on the next chunk while the
-// 16 epilogue warps evaluate the GELU of this one (two S buffers, two H buffers).  TMEM: O at column 0 (C <= 192
+// GEMM1 runs two chunks ahead of GEMM2 (S is released once it sits in registers), so the tensor core works on
+// the coming chunks while the 16 epilogue warps evaluate the GELU of this one (two S buffers, two H buffers).  TMEM: O at column 0 (C <= 192
 // columns), S0 at 256, S1 at 384.  Each W panel is split across the pair (half the rows per CTA), so a CTA
 // streams 2*C*4C bytes of weights per 128 rows — the same as the two unfused GEMMs — and moves NO hidden bytes
 // through HBM: algorithmic traffic is read z + read resid + write out = 6*M*C bytes.
@@ -47,7 +47,9 @@ template <int C> struct FfnCfg {
   static constexpr int H_BYTES = FM * HC * 2;                // one H buffer: two panels
   static constexpr int NOSUB = (C + 63) / 64;                // 64-column output sub-tiles
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = X_BYTES + STAGES * STAGE_BYTES + 2 * H_BYTES + BAR_BYTES + 1024;
+  static constexpr int MAX_HIDDEN = 4 * C;                   // b1 is kept in shared memory (ConvFFN ratio 4)
+  static constexpr int BIAS_BYTES = (MAX_HIDDEN + C) * 4;
+  static constexpr int SMEM_BYTES = X_BYTES + STAGES * STAGE_BYTES + 2 * H_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
   static_assert(C % 32 == 0 && C <= 192, "O accumulators must fit TMEM columns [0, 256)");
   static_assert(2 * H_BYTES >= EPI_WARPS * 4096, "H buffers double as the output staging slabs");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
@@ -83,6 +85,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   auto hempty = [&](int b) { return xempty + 56u + 8u * b; };
   const uint32_t ofull = xempty + 72u, oempty = xempty + 80u;
   const uint32_t tmem_ptr_smem = xempty + 88u;
+  // biases in shared memory: read by every epilogue warp for every chunk (ncu: the per-chunk __ldg of b1 was the
+  // top long-scoreboard stall of the epilogue)
+  float* s_b1 = reinterpret_cast<float*>(smem_ffn + (bar_base - ptx::smem_u32(smem_ffn)) + Cfg::BAR_BYTES);
+  float* s_b2 = s_b1 + Cfg::MAX_HIDDEN;
+  for (int i = threadIdx.x; i < p.hidden; i += FFN_THREADS) s_b1[i] = p.b1[i];
+  for (int i = threadIdx.x; i < C; i += FFN_THREADS) s_b2[i] = p.b2[i];
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = ptx::cluster_ctarank();
@@ -138,28 +146,33 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
         for (int kp = 0; kp < Cfg::KP; ++kp)
           ptx::tma_load_2d_pair(smem_x + kp * PANEL_BYTES, &tmap_x, kp * 64, m0, xfull_leader);
-        // weight panels in exactly the order the MMA warp consumes them: W1(j), then W2(j-1)
-        for (int j = 0; j <= nch; ++j) {
-          if (j < nch) {
-            for (int kp = 0; kp < Cfg::KP; ++kp) {
-              ptx::mbar_wait(wempty(stage), phase ^ 1u);
-              const uint32_t full_leader = ptx::mapa_rank(wfull(stage), 0);
-              ptx::mbar_arrive_expect_tx_cluster(full_leader, Cfg::W1_BYTES);
-              ptx::tma_load_2d_pair(smem_w + stage * Cfg::STAGE_BYTES, &tmap_w1, kp * 64,
-                                    j * HC + static_cast<int>(cta_rank) * (HC / 2), full_leader);
-              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            }
+        // weight panels in exactly the order the MMA warp consumes them:
+        //   W1(0), W1(1), then for every chunk j: W1(j+2) (if any), W2(j)
+        auto load_w1 = [&](int j) {
+          for (int kp = 0; kp < Cfg::KP; ++kp) {
+            ptx::mbar_wait(wempty(stage), phase ^ 1u);
+            const uint32_t full_leader = ptx::mapa_rank(wfull(stage), 0);
+            ptx::mbar_arrive_expect_tx_cluster(full_leader, Cfg::W1_BYTES);
+            ptx::tma_load_2d_pair(smem_w + stage * Cfg::STAGE_BYTES, &tmap_w1, kp * 64,
+                                  j * HC + static_cast<int>(cta_rank) * (HC / 2), full_leader);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          if (j >= 1) {
-            for (int kb = 0; kb < HC / 64; ++kb) {
-              ptx::mbar_wait(wempty(stage), phase ^ 1u);
-              const uint32_t full_leader = ptx::mapa_rank(wfull(stage), 0);
-              ptx::mbar_arrive_expect_tx_cluster(full_leader, Cfg::W2_BYTES);
-              ptx::tma_load_2d_pair(smem_w + stage * Cfg::STAGE_BYTES, &tmap_w2, (j - 1) * HC + kb * 64,
-                                    static_cast<int>(cta_rank) * (C / 2), full_leader);
-              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            }
+        };
+        auto load_w2 = [&](int j) {
+          for (int kb = 0; kb < HC / 64; ++kb) {
+            ptx::mbar_wait(wempty(stage), phase ^ 1u);
+            const uint32_t full_leader = ptx::mapa_rank(wfull(stage), 0);
+            ptx::mbar_arrive_expect_tx_cluster(full_leader, Cfg::W2_BYTES);
+            ptx::tma_load_2d_pair(smem_w + stage * Cfg::STAGE_BYTES, &tmap_w2, j * HC + kb * 64,
+                                  static_cast<int>(cta_rank) * (C / 2), full_leader);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
+        };
+        load_w1(0);
+        if (nch > 1) load_w1(1);
+        for (int j = 0; j < nch; ++j) {
+          if (j + 2 < nch) load_w1(j + 2);
+          load_w2(j);
         }
       }
     }
@@ -171,72 +184,78 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     // the 64 cycles an M=256, N=128 instruction executes for.
     if (cta_rank == 0) {
       constexpr uint32_t idesc1 = ptx::make_idesc_bf16(FPAIR_M, HC);
-      constexpr uint32_t idesc2 = ptx::make_idesc_bf16(FPAIR_M, C);
+      constexpr uint32_t idesc2 = ptx::make_idesc_f16(FPAIR_M, C);  // H and W2 are fp16
       int stage = 0;
       uint32_t phase = 0, t = 0, g1 = 0, g2 = 0;
+      // GEMM1 runs two chunks ahead of GEMM2: S[b] is released as soon as the epilogue has pulled it into
+      // registers, so GEMM1(j+2) executes while GELU(j) is being evaluated and the epilogue never waits for S;
+      // GEMM2(j) follows whenever H[j] is ready.  (With GEMM1 only one chunk ahead and S released at the end of
+      // the GELU, every chunk paid two barrier round trips plus both GEMMs in series: tensor pipe 37 % busy.)
+      auto gemm1 = [&](int j) {
+        const uint32_t b = g1 & 1u;
+        ptx::mbar_wait(sempty(b), ((g1 >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_s = tmem_base + (b ? TMEM_S1 : TMEM_S0);
+#pragma unroll
+        for (int kp = 0; kp < Cfg::KP; ++kp) {
+          ptx::mbar_wait(wfull(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::make_kmajor_sw128_desc(smem_x + kp * PANEL_BYTES);
+          const uint64_t db = ptx::make_kmajor_sw128_desc(smem_w + stage * Cfg::STAGE_BYTES);
+          constexpr int NK_FULL = 4;
+          const int nk = (C - kp * 64) / 16 < NK_FULL ? (C - kp * 64) / 16 : NK_FULL;
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < NK_FULL; ++k)
+              if (k < nk)
+                ptx::umma_bf16_pair(tmem_s, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                                    idesc1, (kp | k) != 0 ? 1u : 0u);
+            ptx::umma_commit_pair(wempty(stage), 3);
+            if (kp == Cfg::KP - 1) {
+              ptx::umma_commit_pair(sfull(b), 3);
+              if (j == nch - 1) ptx::umma_commit_pair(xempty, 3);  // X may be refilled for the next tile
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ++g1;
+      };
+      auto gemm2 = [&](int j, uint32_t t) {
+        const uint32_t b = g2 & 1u;
+        if (j == 0) {  // O of the previous tile must have been drained
+          ptx::mbar_wait(oempty, (t & 1u) ^ 1u);
+          ptx::tc_fence_after();
+        }
+        ptx::mbar_wait(hfull(b), (g2 >> 1) & 1u);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < HC / 64; ++kb) {
+          ptx::mbar_wait(wfull(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::make_kmajor_sw128_desc(smem_h + b * Cfg::H_BYTES + kb * PANEL_BYTES);
+          const uint64_t db = ptx::make_kmajor_sw128_desc(smem_w + stage * Cfg::STAGE_BYTES);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16_pair(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                                  idesc2, (j > 0 || kb != 0 || k != 0) ? 1u : 0u);
+            ptx::umma_commit_pair(wempty(stage), 3);
+            if (kb == HC / 64 - 1) ptx::umma_commit_pair(hempty(b), 3);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ++g2;
+      };
       for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++t) {
         ptx::mbar_wait(xfull, t & 1u);
         ptx::tc_fence_after();
-        for (int j = 0; j <= nch; ++j) {
-          if (j < nch) {
-            // GEMM1: S[b] = X . W1[j]^T
-            const uint32_t b = g1 & 1u;
-            ptx::mbar_wait(sempty(b), ((g1 >> 1) & 1u) ^ 1u);
-            ptx::tc_fence_after();
-            const uint32_t tmem_s = tmem_base + (b ? TMEM_S1 : TMEM_S0);
-#pragma unroll
-            for (int kp = 0; kp < Cfg::KP; ++kp) {
-              ptx::mbar_wait(wfull(stage), phase);
-              ptx::tc_fence_after();
-              const uint64_t da = ptx::make_kmajor_sw128_desc(smem_x + kp * PANEL_BYTES);
-              const uint64_t db = ptx::make_kmajor_sw128_desc(smem_w + stage * Cfg::STAGE_BYTES);
-              constexpr int NK_FULL = 4;
-              const int nk = (C - kp * 64) / 16 < NK_FULL ? (C - kp * 64) / 16 : NK_FULL;
-              if (ptx::elect_one()) {
-#pragma unroll
-                for (int k = 0; k < NK_FULL; ++k)
-                  if (k < nk)
-                    ptx::umma_bf16_pair(tmem_s, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                                        idesc1, (kp | k) != 0 ? 1u : 0u);
-                ptx::umma_commit_pair(wempty(stage), 3);
-                if (kp == Cfg::KP - 1) {
-                  ptx::umma_commit_pair(sfull(b), 3);
-                  if (j == nch - 1) ptx::umma_commit_pair(xempty, 3);  // X may be refilled for the next tile
-                }
-              }
-              __syncwarp();
-              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            }
-            ++g1;
-          }
-          if (j >= 1) {
-            // GEMM2: O += H[b] . W2[:, chunk j-1]^T
-            const uint32_t b = g2 & 1u;
-            if (j == 1) {  // O of the previous tile must have been drained
-              ptx::mbar_wait(oempty, (t & 1u) ^ 1u);
-              ptx::tc_fence_after();
-            }
-            ptx::mbar_wait(hfull(b), (g2 >> 1) & 1u);
-            ptx::tc_fence_after();
-#pragma unroll
-            for (int kb = 0; kb < HC / 64; ++kb) {
-              ptx::mbar_wait(wfull(stage), phase);
-              ptx::tc_fence_after();
-              const uint64_t da = ptx::make_kmajor_sw128_desc(smem_h + b * Cfg::H_BYTES + kb * PANEL_BYTES);
-              const uint64_t db = ptx::make_kmajor_sw128_desc(smem_w + stage * Cfg::STAGE_BYTES);
-              if (ptx::elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::umma_bf16_pair(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
-                                      idesc2, (j > 1 || kb != 0 || k != 0) ? 1u : 0u);
-                ptx::umma_commit_pair(wempty(stage), 3);
-                if (kb == HC / 64 - 1) ptx::umma_commit_pair(hempty(b), 3);
-              }
-              __syncwarp();
-              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            }
-            ++g2;
-          }
+        gemm1(0);
+        if (nch > 1) gemm1(1);
+        for (int j = 0; j < nch; ++j) {
+          if (j + 2 < nch) gemm1(j + 2);
+          gemm2(j, t);
         }
         if (ptx::elect_one()) ptx::umma_commit_pair(ofull, 3);
         __syncwarp();
@@ -261,63 +280,61 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         ptx::tc_fence_after();
         uint32_t r[32];
         ptx::tmem_ld_32x32(lane_base + (b ? TMEM_S1 : TMEM_S0) + static_cast<uint32_t>(grp * 32), r);
-        ptx::mbar_wait(hempty(b), use ^ 1u);  // GEMM2 two chunks ago has finished reading H[b]
         ptx::tmem_ld_wait();
-        float v[32];
-        const float* b1 = p.b1 + j * HC + grp * 32;
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(b ? sempty_leader1 : sempty_leader0);  // S[b] is in registers
+        ptx::mbar_wait(hempty(b), use ^ 1u);  // GEMM2 two chunks ago has finished reading H[b]
+        const float* b1 = s_b1 + j * HC + grp * 32;
+        uint32_t hq[16];  // 32 GELU outputs as fp16 pairs
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1) + q);
-          v[4 * q] = __uint_as_float(r[4 * q]) + b4.x;
-          v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
-          v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
-          v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+          const float4 b4 = reinterpret_cast<const float4*>(b1)[q];
+          hq[2 * q] = gelu_half_f16x2(__uint_as_float(r[4 * q]) + b4.x, __uint_as_float(r[4 * q + 1]) + b4.y);
+          hq[2 * q + 1] = gelu_half_f16x2(__uint_as_float(r[4 * q + 2]) + b4.z, __uint_as_float(r[4 * q + 3]) + b4.w);
         }
-        gelu_half_hybrid(v);
         // H[b]: two K-major panels of 64 columns; this warp's 32 columns are chunks 4*(grp&1) .. +3 of panel grp>>1
         const uint32_t hrow = smem_h + b * Cfg::H_BYTES + static_cast<uint32_t>(grp >> 1) * PANEL_BYTES + row * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int chunk = (grp & 1) * 4 + c;
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + ((chunk ^ (row & 7)) << 4)),
-                       "r"(pack_bf16(v[8 * c], v[8 * c + 1])), "r"(pack_bf16(v[8 * c + 2], v[8 * c + 3])),
-                       "r"(pack_bf16(v[8 * c + 4], v[8 * c + 5])), "r"(pack_bf16(v[8 * c + 6], v[8 * c + 7]))
+                       "r"(hq[4 * c]), "r"(hq[4 * c + 1]), "r"(hq[4 * c + 2]), "r"(hq[4 * c + 3])
                        : "memory");
         }
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();  // generic-proxy writes of H -> visible to the tensor core's async reads
         __syncwarp();
-        if (lane == 0) {
-          ptx::mbar_arrive_cluster(b ? sempty_leader1 : sempty_leader0);
-          ptx::mbar_arrive_cluster(b ? hfull_leader1 : hfull_leader0);
+        if (lane == 0) ptx::mbar_arrive_cluster(b ? hfull_leader1 : hfull_leader0);
+      }
+      // ---- drain O: +b2, +resid, bf16, TMA store (one 64-column sub-tile per warp group; NOSUB <= 3) ----
+      const int sub = grp;
+      const bool has_sub = sub < Cfg::NOSUB;
+      const int col0 = sub * 64;
+      uint4 rr[8];
+      if (has_sub) {  // residual sub-tile (32 rows x 128 B): issued before the wait for O so its latency overlaps
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = i * 32 + lane;
+          const int rrow = idx >> 3, rchunk = idx & 7;
+          const int gm = m0 + ew * 32 + rrow, gc = col0 + rchunk * 8;
+          rr[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (gm < p.M && gc + 8 <= C)
+            rr[i] = __ldg(reinterpret_cast<const uint4*>(p.resid + static_cast<size_t>(gm) * p.ldr + gc));
         }
       }
-      // ---- drain O: +b2, +resid, bf16, TMA store ----
       ptx::mbar_wait(ofull, t & 1u);
       ptx::tc_fence_after();
-      for (int sub = grp; sub < Cfg::NOSUB; sub += 4) {
-        const int col0 = sub * 64;
-        {  // residual sub-tile (32 rows x 128 B): coalesced 16-byte loads into the slab
-          uint4 rr[8];
+      if (has_sub) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int idx = i * 32 + lane;
-            const int rrow = idx >> 3, rchunk = idx & 7;
-            const int gm = m0 + ew * 32 + rrow, gc = col0 + rchunk * 8;
-            rr[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (gm < p.M && gc + 8 <= C)
-              rr[i] = __ldg(reinterpret_cast<const uint4*>(p.resid + static_cast<size_t>(gm) * p.ldr + gc));
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int idx = i * 32 + lane;
-            const int rrow = idx >> 3, rchunk = idx & 7;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + rrow * 128 + ((rchunk ^ (rrow & 7)) << 4)),
-                         "r"(rr[i].x), "r"(rr[i].y), "r"(rr[i].z), "r"(rr[i].w)
-                         : "memory");
-          }
-          __syncwarp();
+        for (int i = 0; i < 8; ++i) {
+          const int idx = i * 32 + lane;
+          const int rrow = idx >> 3, rchunk = idx & 7;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slab + rrow * 128 + ((rchunk ^ (rrow & 7)) << 4)),
+                       "r"(rr[i].x), "r"(rr[i].y), "r"(rr[i].z), "r"(rr[i].w)
+                       : "memory");
         }
+        __syncwarp();
         const uint32_t sbase = slab + lane * 128;
 #pragma unroll
         for (int hp = 0; hp < 2; ++hp) {
@@ -329,7 +346,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           float v[32];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + nb) + q);
+            const float4 b4 = reinterpret_cast<const float4*>(s_b2 + nb)[q];
             v[4 * q] = __uint_as_float(r[4 * q]) + b4.x;
             v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
             v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
@@ -391,7 +408,7 @@ int launch_ffn(const FfnFusedArgs& a, cudaStream_t stream) {
   CUtensorMap tx, tw1, tw2, to;
   if (int rc = make_tmap_bf16(&tx, a.x, a.M, C, C, FM)) return rc;
   if (int rc = make_tmap_bf16(&tw1, a.w1, a.hidden, C, C, HC / 2)) return rc;
-  if (int rc = make_tmap_bf16(&tw2, a.w2, C, a.hidden, a.hidden, C / 2)) return rc;
+  if (int rc = make_tmap_bf16(&tw2, a.w2, C, a.hidden, a.hidden, C / 2)) return rc;  // fp16 bits, same geometry
   if (int rc = make_tmap_bf16(&to, a.out, a.M, C, C, 32)) return rc;
   FfnParams p;
   p.M = a.M; p.hidden = a.hidden; p.b1 = a.b1; p.b2 = a.b2;
@@ -407,7 +424,7 @@ int launch_ffn(const FfnFusedArgs& a, cudaStream_t stream) {
 }  // namespace
 
 bool ffn_fused_supported(int dtype, int C, int hidden) {
-  return dtype == DT_BF16 && (C == 96 || C == 192) && hidden % HC == 0 && hidden >= HC;
+  return dtype == DT_BF16 && (C == 96 || C == 192) && hidden % HC == 0 && hidden >= HC && hidden <= 4 * C;
 }
 
 int ffn_fused(const FfnFusedArgs& a, cudaStream_t stream) {

@@ -37,7 +37,7 @@ struct FfnFusedArgs {
   const void* x = nullptr;      // [M, C]
   const void* w1 = nullptr;     // [hidden, C]  (x 1/2)
   const float* b1 = nullptr;    // [hidden]     (x 1/2)
-  const void* w2 = nullptr;     // [C, hidden]
+  const void* w2 = nullptr;     // [C, hidden] as FP16 (the on-chip hidden tensor is fp16)
   const float* b2 = nullptr;    // [C]
   const void* resid = nullptr;  // [M, C], may alias out
   void* out = nullptr;          // [M, C]

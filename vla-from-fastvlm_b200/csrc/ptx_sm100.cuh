@@ -224,6 +224,10 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2u) << 61;                    // SWIZZLE_128B
   return d;
 }
+// fp16 x fp16 -> fp32 (A/B format fields 0), both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
 // bf16 x bf16 -> fp32, both operands K-major, MMA shape M x N (K = 16 per instruction).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4)                              // accumulator format f32

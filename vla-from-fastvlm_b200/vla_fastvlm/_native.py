@@ -264,7 +264,7 @@ def op_ffn_fused(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and resid.is_contiguous()
     w1h = (w1.float() * 0.5).to(torch.bfloat16).contiguous()
     b1h = (b1.float() * 0.5).contiguous()
-    w2c = w2.to(torch.bfloat16).contiguous()
+    w2c = w2.to(torch.float16).contiguous()  # the on-chip hidden tensor and fc2 run in fp16
     b2c = b2.float().contiguous()
     if out is None:
         out = torch.empty_like(x)
