@@ -356,6 +356,29 @@ def test_se_gelu(native, dtype, B, HW, Cc, Cr):
     _close(out, ref, BF16_TOL if dtype == torch.bfloat16 else F32_TOL, "se_gelu")
 
 
+@pytest.mark.parametrize("M,K,hidden", [(640, 384, 1536), (300, 96, 384), (4096, 768, 3072)])
+def test_gemm_fp16_hidden_chain(native, M, K, hidden):
+    """ConvFFN as two GEMMs with the hidden tensor in fp16: fc1 (bf16 operands, pre-halved, act 5 -> fp16 GELU
+    output) then fc2 (fp16 x fp16 MMA, bf16 output + residual), against fp64 math."""
+    dev = _dev()
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    w1 = (torch.randn(hidden, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    b1 = (0.5 * torch.randn(hidden, generator=g)).to(dev)
+    w2 = (torch.randn(K, hidden, generator=g) / math.sqrt(hidden)).to(dev).bfloat16()
+    b2 = torch.randn(K, generator=g).to(dev)
+    resid = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    h = native.op_gemm(x, (w1.float() * 0.5).bfloat16(), bias=b1 * 0.5, act=5)
+    assert h.dtype == torch.float16
+    href = F.gelu(x.double() @ w1.double().t() + b1.double())
+    _close(h, href.float(), 1.0 / 512, "fp16 GELU hidden")
+    # large-magnitude pre-activations stay exact in the saturated regions
+    out = native.op_gemm(h, w2.half(), bias=b2, resid=resid)
+    assert out.dtype == torch.bfloat16
+    ref = (h.double() @ w2.double().t() + b2.double() + resid.double()).float()
+    _close(out, ref, BF16_TOL, "fc2 on fp16 operands")
+
+
 def test_gemm_bf16_gelu_large_magnitudes(native):
     """The MUFU-based GELU must stay exact-in-bf16 far outside the fitted range (|x| up to ~300)."""
     dev = _dev()

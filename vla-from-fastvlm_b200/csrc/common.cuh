@@ -31,7 +31,9 @@ const char* last_error();
   } while (0)
 
 // ACT_GELU_HALF: the operand is x/2 (weights and bias pre-scaled by 1/2 at pack time), result gelu(x)
-enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_RELU = 3, ACT_GELU_HALF = 4 };
+// ACT_GELU_HALF_F16 (bf16 tensor-core GEMM only): as ACT_GELU_HALF, but the result is stored as FP16 — for hidden
+// tensors whose only consumer is another of our GEMMs run with fp16 operands (GemmArgs::ab_f16)
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_RELU = 3, ACT_GELU_HALF = 4, ACT_GELU_HALF_F16 = 5 };
 
 // ---- scalar conversions -------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }

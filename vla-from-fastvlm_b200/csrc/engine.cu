@@ -351,8 +351,9 @@ int Engine::pack_vision() {
       b2[n] = f2b->data[n] * l;
     }
     if (int rc = make_gemm(&blk->fc2, w2, d, hd, &b2)) return rc;
-    if (ffn_fused_supported(cfg.dtype, d, hd)) {
-      // the fused ConvFFN kernel keeps its hidden tensor in fp16 and runs fc2 as an fp16 x fp16 MMA
+    if (cfg.dtype == FVLA_BF16) {
+      // the ConvFFN hidden tensor is fp16 (on chip in the fused kernel, in HBM otherwise): GELU runs on packed
+      // half pairs and fc2 is an fp16 x fp16 MMA
       std::vector<__half> h(w2.size());
       for (size_t i = 0; i < w2.size(); ++i) h[i] = __float2half_rn(w2[i]);
       void* p = nullptr;
@@ -633,7 +634,7 @@ int Engine::tap(int stage, const void* src, size_t bytes, size_t off, cudaStream
 // Forward
 // ---------------------------------------------------------------------------------------------
 int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, const void* resid,
-                     bool swiglu, cudaStream_t s) {
+                     bool swiglu, cudaStream_t s, bool ab_f16) {
   GemmArgs g;
   g.A = A; g.lda = w.K;
   g.W = w.w; g.ldw = w.K;
@@ -643,6 +644,7 @@ int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, con
   g.resid = resid; g.ldr = w.N;
   g.act = (act == ACT_GELU && w.half_in) ? static_cast<int>(ACT_GELU_HALF) : act;
   g.swiglu = swiglu ? 1 : 0;
+  g.ab_f16 = ab_f16 ? 1 : 0;
   ++launches;
   const double fl = 2.0 * M * static_cast<double>(w.N) * w.K;
   flops += fl;
@@ -654,7 +656,7 @@ int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, con
                            static_cast<double>(M) * g.ldd + (resid ? static_cast<double>(M) * w.N : 0.0));
     prof_end(std::string(prof_scope_) + "gemm M" + std::to_string(M) + " N" + std::to_string(w.N) + " K" +
                  std::to_string(w.K) + (swiglu ? " swiglu" : "") + (resid ? " +res" : "") +
-                 (act == ACT_GELU ? " gelu" : ""),
+                 ((act == ACT_GELU || act == ACT_GELU_HALF_F16) ? " gelu" : ""),
              fl, by, s);
   }
   return rc;
@@ -678,6 +680,12 @@ int Engine::run_ffn(const VisBlock& blk, const void* z, void* hid, void* out_res
     prof_end("vis.ffn_fused M" + std::to_string(M) + " C" + std::to_string(d) + " H" + std::to_string(hd), fl,
              static_cast<double>(esz()) * (3.0 * M * d + 2.0 * hd * d), s);
     return rc;
+  }
+  if (cfg.dtype == FVLA_BF16 && blk.fc1.half_in && blk.fc2.w_f16 != nullptr) {
+    if (int rc = run_gemm(blk.fc1, z, hid, M, ACT_GELU_HALF_F16, nullptr, false, s)) return rc;
+    GemmW fc2h = blk.fc2;
+    fc2h.w = blk.fc2.w_f16;
+    return run_gemm(fc2h, hid, out_resid, M, ACT_NONE, out_resid, false, s, /*ab_f16=*/true);
   }
   if (int rc = run_gemm(blk.fc1, z, hid, M, ACT_GELU, nullptr, false, s)) return rc;
   return run_gemm(blk.fc2, hid, out_resid, M, ACT_NONE, out_resid, false, s);

@@ -18,7 +18,7 @@ struct HostTensor {
 
 struct GemmW {  // packed nn.Linear / 1x1 conv
   void* w = nullptr;          // [N, K] in engine dtype
-  void* w_f16 = nullptr;      // same matrix as fp16, only for fc2 of blocks served by the fused ConvFFN kernel
+  void* w_f16 = nullptr;      // same matrix as fp16: ConvFFN fc2 (bf16 mode), whose hidden operand is stored as fp16
   const float* bias = nullptr;  // [N] fp32 or null
   int N = 0, K = 0;
   bool half_in = false;       // weights+bias pre-scaled by 1/2: the GELU epilogue takes x/2 (ACT_GELU_HALF)
@@ -95,7 +95,7 @@ class Engine {
   int tap(int stage, const void* src, size_t bytes, size_t dst_offset_bytes, cudaStream_t s);
 
   int run_gemm(const GemmW& w, const void* A, void* D, int M, int act, const void* resid, bool swiglu,
-               cudaStream_t s);
+               cudaStream_t s, bool ab_f16 = false);
   int run_ffn(const VisBlock& blk, const void* z, void* hid, void* out_resid, int M, cudaStream_t s);
   int run_dw(const DwW& w, const void* in, void* out, int B, int H, int W, cudaStream_t s);
   int vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats, cudaStream_t s);

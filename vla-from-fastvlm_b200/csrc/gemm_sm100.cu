@@ -57,6 +57,7 @@ struct EpiParams {
   const __nv_bfloat16* resid;  // [M, ldr] or null (added after the activation)
   int ldr;
   int act;
+  int ab_f16;                  // operands are fp16 (instruction descriptor formats), else bf16
 };
 
 using namespace epi;
@@ -148,7 +149,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // warp-uniform control flow, tcgen05 instructions under elect_one: descriptors stay in uniform registers and
     // the four UTCHMMAs of a k-block issue back to back
     if (cta_rank == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(PAIR_M, BLOCK_N);
+      const uint32_t idesc = p.ab_f16 ? ptx::make_idesc_f16(PAIR_M, BLOCK_N) : ptx::make_idesc_bf16(PAIR_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -204,17 +205,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       float rs = 1.0f;
       if (p.row_scale != nullptr && m < p.M) rs = __ldg(p.row_scale + m);
 
-      ptx::mbar_wait(tfull_bar(acc), acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t tmem_acc =
-          tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
-
-#pragma unroll 1
-      for (int sub = 0; sub < NUM_SUB; ++sub, ++sub_counter) {
-        if ((sub_counter & 3u) != static_cast<uint32_t>(grp)) continue;
-        const int acc_col0 = sub * ACC_PER_SUB;                    // first accumulator column
-        const int out_col0 = (SWIGLU ? (n0 / 2) : n0) + sub * 64;  // first output column
-        if (out_col0 >= n_out_total) continue;                     // whole sub-tile out of range
+      // This warp's sub-tile of the tile (the rotation gives every warp at most one): known before the
+      // accumulator is ready, so the slab hand-back and the residual loads are issued under the wait for the MMAs.
+      const int sub = static_cast<int>((static_cast<uint32_t>(grp) - sub_counter) & 3u);
+      sub_counter += NUM_SUB;
+      const int acc_col0 = sub * ACC_PER_SUB;                    // first accumulator column
+      const int out_col0 = (SWIGLU ? (n0 / 2) : n0) + sub * 64;  // first output column
+      const bool has_sub = sub < NUM_SUB && out_col0 < n_out_total;
+      if (has_sub) {
         // the TMA store this warp issued from its slab last time must have finished reading it
         if (lane == 0) ptx::tma_store_wait_read<0>();
         __syncwarp();
@@ -241,11 +239,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
           __syncwarp();
         }
+      }
 
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t tmem_acc =
+          tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+
+      if (has_sub) {
 #pragma unroll
         for (int hp = 0; hp < ACC_PER_SUB / 32; ++hp) {
           uint32_t r[32];
           ptx::tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(acc_col0 + hp * 32), r);
+          // bias for these 32 columns: issued under the TMEM load so the two latencies overlap
+          const int nb = n0 + acc_col0 + hp * 32;  // global column of v[0]
+          const bool bias_vec = !SWIGLU && p.bias != nullptr && nb + 32 <= p.N;
+          float4 bq[8];
+          if (bias_vec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j);
+          }
           ptx::tmem_ld_wait();
           float v[32];
           if (p.row_scale != nullptr) {
@@ -273,19 +286,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                            : "memory");
             }
           } else {
-            const int nb = n0 + acc_col0 + hp * 32;  // global column of v[0]
             if (p.bias != nullptr) {
-              if (nb + 32 <= p.N) {
+              if (bias_vec) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j);
-                  v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                  v[4 * j] += bq[j].x; v[4 * j + 1] += bq[j].y; v[4 * j + 2] += bq[j].z; v[4 * j + 3] += bq[j].w;
                 }
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                   if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
               }
+            }
+            if (p.act == ACT_GELU_HALF_F16) {
+              // fp16 hidden tensor: the whole activation on packed half pairs (epilogue_math.cuh), no residual
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int chunk = hp * 4 + c;
+                const uint32_t dst = sbase + ((chunk ^ (lane & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                             "r"(gelu_half_f16x2(v[8 * c], v[8 * c + 1])),
+                             "r"(gelu_half_f16x2(v[8 * c + 2], v[8 * c + 3])),
+                             "r"(gelu_half_f16x2(v[8 * c + 4], v[8 * c + 5])),
+                             "r"(gelu_half_f16x2(v[8 * c + 6], v[8 * c + 7]))
+                             : "memory");
+              }
+              continue;
             }
             if (p.act == ACT_GELU_HALF) {
               gelu_half_hybrid(v);
@@ -412,7 +438,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   EpiParams ep;
   ep.M = g.M; ep.N = g.N; ep.K = g.K;
   ep.bias = g.bias; ep.row_scale = g.row_scale;
-  ep.resid = static_cast<const __nv_bfloat16*>(g.resid); ep.ldr = g.ldr; ep.act = g.act;
+  ep.resid = static_cast<const __nv_bfloat16*>(g.resid); ep.ldr = g.ldr; ep.act = g.act; ep.ab_f16 = g.ab_f16;
   const int tiles = ceil_div(g.M, PAIR_M) * ceil_div(g.N, BLOCK_N);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
@@ -453,6 +479,8 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
                  "SwiGLU epilogue takes interleaved gate/up columns and no bias/residual/activation");
   }
   if (g.resid != nullptr) FVLA_REQUIRE(g.ldr % 8 == 0, "residual pitch must be a multiple of 8");
+  if (g.act == ACT_GELU_HALF_F16)
+    FVLA_REQUIRE(g.resid == nullptr && !g.swiglu, "the fp16-output GELU epilogue takes no residual");
   const int bn = g.block_n > 0 ? g.block_n : pick_block_n(g.N, g.swiglu != 0);
   if (g.swiglu) {
     switch (bn) {

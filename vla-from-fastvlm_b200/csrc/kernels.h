@@ -23,6 +23,7 @@ struct GemmArgs {
   int act = 0;                            // Act enum
   int swiglu = 0;                         // columns are interleaved (gate, up): out = silu(g) * u
   int block_n = 0;                        // 0 = auto (bf16 path only)
+  int ab_f16 = 0;                         // bf16 path: A and W hold FP16 bits (fp16 x fp16 -> fp32 MMA)
 };
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);  // tcgen05 + TMA + TMEM
 int gemm_f32(const GemmArgs& g, cudaStream_t stream);   // FFMA, fp32 parity mode

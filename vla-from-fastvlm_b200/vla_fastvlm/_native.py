@@ -20,6 +20,7 @@ _CSRC = _HERE.parent / "csrc"
 
 FVLA_F32, FVLA_BF16, FVLA_U8 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_SILU, ACT_RELU = 0, 1, 2, 3
+ACT_GELU_HALF, ACT_GELU_HALF_F16 = 4, 5  # operand pre-halved; 5 stores the result as fp16
 POOL_LAST_TOKEN, POOL_MEAN = 0, 1
 IMAGE_TOKEN_INDEX = -200
 MAX_VIS_STAGES = 8
@@ -212,18 +213,24 @@ def op_gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
             resid: Optional[torch.Tensor] = None, act: int = ACT_NONE, swiglu: bool = False,
             row_scale: Optional[torch.Tensor] = None, block_n: int = 0,
             out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """D = act(row_scale * A @ W^T + bias) + resid, A [M,K], W [N,K]."""
+    """D = act(row_scale * A @ W^T + bias) + resid, A [M,K], W [N,K].
+
+    fp16 operands (A and W both torch.float16) select the tensor-core path with fp16 x fp16 MMAs; the output is
+    bf16 unless act == ACT_GELU_HALF_F16 (5), whose result is fp16 (the ConvFFN hidden tensor)."""
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1] and a.dtype == w.dtype
     assert a.is_contiguous() and w.is_contiguous()
     M, K = a.shape
     N = w.shape[0]
     n_out = N // 2 if swiglu else N
+    ab_f16 = a.dtype == torch.float16
+    code = dtype_code(torch.bfloat16) if ab_f16 else dtype_code(a.dtype)
     if out is None:
-        out = torch.empty((M, n_out), device=a.device, dtype=a.dtype)
-    check(load().fvla_op_gemm(dtype_code(a.dtype), ptr(a), K, ptr(w), K, ptr(out), out.stride(0), M, N,
+        odt = torch.float16 if act == ACT_GELU_HALF_F16 else (torch.bfloat16 if ab_f16 else a.dtype)
+        out = torch.empty((M, n_out), device=a.device, dtype=odt)
+    check(load().fvla_op_gemm(code, ptr(a), K, ptr(w), K, ptr(out), out.stride(0), M, N,
                               K, ptr(bias), ptr(row_scale), ptr(resid),
-                              resid.stride(0) if resid is not None else 0, act, int(swiglu), block_n,
-                              stream_ptr()), "fvla_op_gemm")
+                              resid.stride(0) if resid is not None else 0, act, int(swiglu) | (2 if ab_f16 else 0),
+                              block_n, stream_ptr()), "fvla_op_gemm")
     return out
 
 
