@@ -160,3 +160,27 @@ def test_engine_errors():
     two[0, 1] = -200
     with pytest.raises(N.NativeError, match="placeholder"):
         eng2.forward(images.cuda(), two, mask.sum(1), states=states.cuda())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_small_batch_graph_replay_matches_eager(dtype):
+    """Batches <= 8 run as a CUDA graph from the third call on (eager warm-up, capture, replay).  Every call —
+    eager, captured and replayed, with fresh inputs each time and a prompt-length change in between — must give
+    exactly what the same samples give inside a batch of 12, which always runs eagerly."""
+    _need_gpu()
+    arch, sd, hsd = tiny_weights(0)
+    eng = make_engine(arch, sd, hsd, dtype)
+    dev = eng.device
+    images, states, ids, mask = make_inputs(12, 120, 160, 9, arch.text.vocab, TINY_HEAD["state_dim"], seed=11)
+    lens = mask.sum(1)
+    big = eng.forward(images.to(dev), ids, lens, states=states.to(dev)).float().cpu()
+    assert torch.isfinite(big).all()
+    for rep, lo in enumerate([0, 2, 4, 6, 8, 0]):
+        sl = slice(lo, lo + 2)
+        got = eng.forward(images[sl].to(dev), ids[sl], lens[sl], states=states[sl].to(dev)).float().cpu()
+        assert torch.equal(got, big[sl]), f"call {rep} (samples {lo}..{lo + 1}) differs from the eager batch"
+    # a different token width (new T') gets its own graph; results still match
+    ids2 = torch.cat([ids, torch.zeros(12, 3, dtype=ids.dtype)], dim=1)
+    for rep in range(3):
+        got = eng.forward(images[:1].to(dev), ids2[:1], lens[:1], states=states[:1].to(dev)).float().cpu()
+        assert torch.equal(got, big[:1]), f"wider prompt buffer, call {rep}"

@@ -25,6 +25,8 @@ std::string S(const char* p, const std::string& rest) { return std::string(p) + 
 Engine::Engine(const fvla_config& c) : cfg(c) {}
 
 Engine::~Engine() {
+  clear_graphs();
+  if (graph_stream_ != nullptr) cudaStreamDestroy(graph_stream_);
   for (void* p : dev_allocs_) cudaFree(p);
   for (auto& kv : ws_.bufs) cudaFree(kv.second.first);
   for (auto& p : prof_) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
@@ -605,6 +607,7 @@ int Engine::ensure(const std::string& name, size_t bytes, void** out) {
   }
   void* p = nullptr;
   FVLA_CUDA_CHECK(cudaMalloc(&p, bytes));
+  clear_graphs();  // captured launches hold workspace pointers
   ws_.bufs[name] = {p, bytes};
   ws_.total += bytes;
   *out = p;
@@ -938,6 +941,22 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
   FVLA_CUDA_CHECK(cudaMemcpyAsync(d_pidx, pidx.data(), pidx.size() * 4, cudaMemcpyHostToDevice, s));
   FVLA_CUDA_CHECK(cudaMemcpyAsync(d_lens, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice, s));
 
+  // ---- CUDA-graph replay for small batches (the b=1 select_action latency is launch-bound: ~390 launches) ----
+  static const bool graphs_on = std::getenv("FVLA_DISABLE_GRAPHS") == nullptr;
+  const bool graphable = graphs_on && B <= kGraphMaxBatch && !profile_ && taps_.empty() && a.pooled == nullptr &&
+                         a.states != nullptr && a.actions != nullptr && (a.images != nullptr || !any_image);
+  if (!graphable) return launch_all(a, B, Tm, any_image, s);
+  return forward_graph(a, B, Tm, any_image, s);
+}
+
+// Kernel sequence of one forward; reads the splice plan / pool indices from the workspace (uploaded by forward()).
+// Pure stream-ordered launches (no allocation, no synchronisation): capturable into a CUDA graph.
+int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image, cudaStream_t s) {
+  const int H = cfg.hidden, nimg = n_img_tokens();
+  const size_t e = esz();
+  int* d_plan = static_cast<int*>(ws_.bufs["plan"].first);
+  int* d_pidx = static_cast<int*>(ws_.bufs["pool_idx"].first);
+  int* d_lens = static_cast<int*>(ws_.bufs["lens"].first);
   // ---- FastViTHD + projector ----
   void* feats = ws_.bufs["feats"].first;
   void* proj_h = ws_.bufs["proj_h"].first;
@@ -1041,6 +1060,80 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
     if (int rc = tap(FVLA_TAP_STATE_FEAT, ts, static_cast<size_t>(B) * cfg.hidden_dim * 4, 0, s)) return rc;
     if (int rc = tap(FVLA_TAP_FUSED, tf, static_cast<size_t>(B) * cfg.fusion_dim * 4, 0, s)) return rc;
   }
+  return 0;
+}
+
+void Engine::clear_graphs() {
+  for (auto& kv : graphs_)
+    if (kv.second.exec != nullptr) cudaGraphExecDestroy(kv.second.exec);
+  graphs_.clear();
+}
+
+// Inputs are copied into engine-owned staging buffers so that the captured launches never hold caller pointers;
+// the first call with a new geometry runs eagerly (one-time attribute / static initialisation), the second is
+// captured on an internal stream and instantiated, later calls are one cudaGraphLaunch into the caller's stream.
+int Engine::forward_graph(const fvla_forward_args& a, int B, int Tm, bool any_image, cudaStream_t s) {
+  const size_t img_bytes = a.images != nullptr
+                               ? static_cast<size_t>(B) * a.img_c * a.img_h * a.img_w * dtype_size(a.img_dtype)
+                               : 0;
+  const size_t st_bytes = static_cast<size_t>(B) * cfg.state_dim * 4;
+  const size_t act_bytes = static_cast<size_t>(B) * cfg.action_dim * 4;
+  void *in_img = nullptr, *in_st = nullptr;
+  if (img_bytes != 0)
+    if (int rc = ensure("in_images", img_bytes, &in_img)) return rc;
+  if (int rc = ensure("in_states", st_bytes, &in_st)) return rc;
+  float* out_act = static_cast<float*>(ws_.bufs["actions"].first);
+
+  fvla_forward_args g = a;
+  g.images = in_img;
+  g.states = static_cast<const float*>(in_st);
+  g.actions = out_act;
+  if (img_bytes != 0) FVLA_CUDA_CHECK(cudaMemcpyAsync(in_img, a.images, img_bytes, cudaMemcpyDeviceToDevice, s));
+  FVLA_CUDA_CHECK(cudaMemcpyAsync(in_st, a.states, st_bytes, cudaMemcpyDeviceToDevice, s));
+
+  // everything launch_all's control flow and kernel arguments depend on
+  std::string key;
+  auto add = [&key](const void* p, size_t n) { key.append(static_cast<const char*>(p), n); };
+  const int ints[] = {B, Tm, any_image ? 1 : 0, a.img_c, a.img_h, a.img_w, a.img_dtype, a.img_nhwc, a.letterbox,
+                      a.normalize, a.images != nullptr ? 1 : 0};
+  add(ints, sizeof(ints));
+  const float fl[] = {a.pad_value, a.img_scale, a.mean[0], a.mean[1], a.mean[2], a.inv_std[0], a.inv_std[1], a.inv_std[2]};
+  add(fl, sizeof(fl));
+
+  GraphEntry& ent = graphs_[key];
+  int rc = 0;
+  if (ent.exec != nullptr) {
+    FVLA_CUDA_CHECK(cudaGraphLaunch(ent.exec, s));
+    launches = ent.launches;
+    flops = ent.flops;
+  } else if (ent.state == 0 || ent.state == 3) {
+    ent.state = ent.state == 0 ? 1 : 3;  // 1: warmed up eagerly, capture next time; 3: capture failed, stay eager
+    rc = launch_all(g, B, Tm, any_image, s);
+  } else {
+    if (graph_stream_ == nullptr) FVLA_CUDA_CHECK(cudaStreamCreateWithFlags(&graph_stream_, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(graph_stream_, cudaStreamCaptureModeThreadLocal);
+    if (ce == cudaSuccess) {
+      rc = launch_all(g, B, Tm, any_image, graph_stream_);
+      ce = cudaStreamEndCapture(graph_stream_, &graph);
+    }
+    if (ce == cudaSuccess && rc == 0 && graph != nullptr)
+      ce = cudaGraphInstantiate(&ent.exec, graph, 0);
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    if (ce != cudaSuccess || rc != 0 || ent.exec == nullptr) {
+      cudaGetLastError();  // clear the sticky capture error, fall back to eager launches for this geometry
+      ent.exec = nullptr;
+      ent.state = 3;
+      rc = launch_all(g, B, Tm, any_image, s);
+    } else {
+      ent.state = 2;
+      ent.launches = launches;
+      ent.flops = flops;
+      FVLA_CUDA_CHECK(cudaGraphLaunch(ent.exec, s));
+    }
+  }
+  if (rc != 0) return rc;
+  FVLA_CUDA_CHECK(cudaMemcpyAsync(a.actions, out_act, act_bytes, cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 

@@ -99,6 +99,13 @@ class Engine {
   int run_ffn(const VisBlock& blk, const void* z, void* hid, void* out_resid, int M, cudaStream_t s);
   int run_dw(const DwW& w, const void* in, void* out, int B, int H, int W, cudaStream_t s);
   int vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats, cudaStream_t s);
+  int launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image, cudaStream_t s);
+  int forward_graph(const fvla_forward_args& a, int B, int Tm, bool any_image, cudaStream_t s);
+  void clear_graphs();
+  static constexpr int kGraphMaxBatch = 8;  // larger batches are GPU-bound; their inputs are not worth re-staging
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int state = 0; int64_t launches = 0; double flops = 0.0; };
+  std::map<std::string, GraphEntry> graphs_;
+  cudaStream_t graph_stream_ = nullptr;
 
   size_t esz() const { return dtype_size(cfg.dtype); }
   int n_img_tokens() const;
