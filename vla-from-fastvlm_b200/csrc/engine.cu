@@ -761,6 +761,7 @@ int Engine::reserve(int B, int n_tokens) {
   if (int rc = ensure("actions", static_cast<size_t>(B) * cfg.action_dim * 4, &p)) return rc;
   if (int rc = ensure("tap_state", static_cast<size_t>(B) * cfg.hidden_dim * 4, &p)) return rc;
   if (int rc = ensure("tap_fused", static_cast<size_t>(B) * cfg.fusion_dim * 4, &p)) return rc;
+  if (int rc = ensure("head_x1", static_cast<size_t>(B) * cfg.fusion_dim * 4, &p)) return rc;
   // rotary tables for every merged position (HF default rope init, fp32)
   if (rope_len_ < static_cast<int>(Tm)) {
     const int half = cfg.head_dim / 2;
@@ -1055,7 +1056,8 @@ int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image
                         static_cast<double>(cfg.fusion_dim) * cfg.fusion_dim +
                         static_cast<double>(cfg.fusion_dim) * cfg.action_dim);
     prof_begin(s);
-    if (int rc = action_head(cfg.dtype, head_, pooled, a.states, a.actions, ts, tf, B, s)) return rc;
+    float* tx = static_cast<float*>(ws_.bufs["head_x1"].first);
+    if (int rc = action_head(cfg.dtype, head_, pooled, a.states, a.actions, ts, tx, tf, B, s)) return rc;
     prof_end("head.action_head", 0.0, 0.0, s);
     if (int rc = tap(FVLA_TAP_STATE_FEAT, ts, static_cast<size_t>(B) * cfg.hidden_dim * 4, 0, s)) return rc;
     if (int rc = tap(FVLA_TAP_FUSED, tf, static_cast<size_t>(B) * cfg.fusion_dim * 4, 0, s)) return rc;

@@ -447,10 +447,13 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   return 0;
 }
 
-// Pick the N tile with the least padded work per unit of measured tile efficiency: narrow tiles move more
-// operand bytes per flop through the same smem ring (BLOCK_N = 128 sustains ~0.78 of the 256-wide rate on a
-// long-K GEMM, 64 about half), so e.g. N = 896 runs faster as 4 x 256 (12 % padding) than as 7 x 128.
-int pick_block_n(int N, bool swiglu) {
+// Pick the N tile by modelled time: waves over the 74 CTA pairs x time per tile.  Per-tile time ~ BLOCK_N / eff
+// (narrow tiles move more operand bytes per flop through the same smem ring: BLOCK_N = 128 sustains ~0.78 of the
+// 256-wide rate on a long-K GEMM, 64 about half) plus a fixed pipeline fill / epilogue term.  For large M this
+// reduces to "least padded work per unit efficiency" (N = 896 -> 4 x 256, not 7 x 128); for small M (the b=1
+// select_action prefill, M = 272) it prefers narrow tiles that spread the N dimension over more SMs — a 2 x 4 grid
+// of 256-wide tiles leaves 66 of 74 pairs idle while each busy pair walks the whole K loop.
+int pick_block_n(int M, int N, bool swiglu) {
   const int cands_plain[4] = {256, 192, 128, 64};
   const double eff_plain[4] = {1.0, 0.96, 0.78, 0.5};
   const int cands_glu[2] = {256, 128};
@@ -458,11 +461,15 @@ int pick_block_n(int N, bool swiglu) {
   const int* cands = swiglu ? cands_glu : cands_plain;
   const double* eff = swiglu ? eff_glu : eff_plain;
   const int nc = swiglu ? 2 : 4;
+  const int pairs = num_sms() / 2;
+  const long long m_tiles = ceil_div(M, PAIR_M);
   int best = cands[0];
   double best_cost = -1.0;
   for (int i = 0; i < nc; ++i) {
     const int bn = cands[i];
-    const double cost = static_cast<double>(ceil_div(N, bn)) * bn / eff[i];
+    const long long tiles = m_tiles * ceil_div(N, bn);
+    const double waves = static_cast<double>((tiles + pairs - 1) / pairs);
+    const double cost = waves * (bn / eff[i] + 48.0);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -481,7 +488,7 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (g.resid != nullptr) FVLA_REQUIRE(g.ldr % 8 == 0, "residual pitch must be a multiple of 8");
   if (g.act == ACT_GELU_HALF_F16)
     FVLA_REQUIRE(g.resid == nullptr && !g.swiglu, "the fp16-output GELU epilogue takes no residual");
-  const int bn = g.block_n > 0 ? g.block_n : pick_block_n(g.N, g.swiglu != 0);
+  const int bn = g.block_n > 0 ? g.block_n : pick_block_n(g.M, g.N, g.swiglu != 0);
   if (g.swiglu) {
     switch (bn) {
       case 256: return launch_gemm<256, true>(g, stream);

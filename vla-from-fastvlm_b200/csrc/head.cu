@@ -3,8 +3,8 @@
 //   f = cat(pooled, s)
 //   f = SiLU(Linear(Dropout(SiLU(LayerNorm(Linear(f))))))  fusion   (Dropout is identity in eval)
 //   a = Linear(f)                                          action_head
-// A CTA carries R batch rows through all four matrices; activations stay in shared memory, each warp
-// streams weight rows as 128-bit vectors and reduces R dot products at once.
+// A cluster of 8 CTAs carries R batch rows through all four matrices, each CTA owning an eighth of every layer's
+// output neurons; each warp streams weight rows as 128-bit vectors and reduces R dot products at once.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -53,10 +53,18 @@ __device__ __forceinline__ void warp_dot_rows(const T* __restrict__ wbase, int l
     for (int r = 0; r < R; ++r) acc[j][r] = warp_sum(acc[j][r]);
 }
 
+// One kernel, one thread-block CLUSTER of 8 CTAs per R batch rows: every matrix is split 8 ways over its output
+// neurons, so 8 SMs stream the 6 MB of head weights for a row group instead of one (at b = 1 the single-CTA version
+// took 0.37 ms = 7 % of the whole select_action; the weights come from L2 at a few bytes per clock per SM, so the
+// only lever is more SMs per row).  Layer outputs are exchanged through small global scratch rows (they double as
+// the parity taps) ordered by cluster-scope release/acquire barriers; LayerNorm statistics are recomputed by every
+// CTA from the full row (1024 values).
+constexpr int HEAD_CL = 8;
+
 template <typename T, int R>
-__global__ void __launch_bounds__(256)
+__global__ void __cluster_dims__(HEAD_CL, 1, 1) __launch_bounds__(256)
 action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float* __restrict__ states,
-                   float* __restrict__ actions, float* tap_state, float* tap_fused, int B) {
+                   float* __restrict__ actions, float* state_feat, float* x1_scratch, float* fused, int B) {
   extern __shared__ __align__(16) float sh[];
   const int H = w.H, S = w.S, Hd = w.Hd, F = w.F, A = w.A;
   const int KC = H + Hd;
@@ -64,12 +72,17 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
   float* x1 = cat + R * KC;     // [R][F]
   float* x2 = x1 + R * F;       // [R][F]
   float* sln = x2 + R * F;      // [R][S] normalised state
-  const int r0 = blockIdx.x * R;
+  const int crank = static_cast<int>(blockIdx.x % HEAD_CL);
+  const int r0 = static_cast<int>(blockIdx.x / HEAD_CL) * R;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwarps = blockDim.x >> 5;
   constexpr int NC = 4;
+  auto cluster_sync = [] {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  };
 
-  // ---- LayerNorm(state) (eps 1e-5, biased variance) ----
+  // ---- LayerNorm(state) (eps 1e-5, biased variance); every CTA of the cluster needs all of it ----
   if (warp < R) {
     const int b = r0 + warp;
     if (b < B) {
@@ -95,10 +108,12 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
     cat[r * KC + c] = b < B ? pooled[static_cast<size_t>(b) * H + c] : 0.f;
   }
   __syncthreads();
-  // ---- state projection + SiLU -> cat[:, H:] ----
+  // ---- state projection + SiLU: this CTA's slice of the Hd outputs -> state_feat (global) ----
   {
     const T* ws = static_cast<const T*>(w.w_state);
-    for (int n = tid; n < Hd; n += blockDim.x) {
+    const int per = (Hd + HEAD_CL - 1) / HEAD_CL;
+    const int n_end = min(Hd, (crank + 1) * per);
+    for (int n = crank * per + tid; n < n_end; n += blockDim.x) {
       float acc[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = w.b_state[n];
@@ -108,33 +123,43 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
         for (int r = 0; r < R; ++r) acc[r] = fmaf(wv, sln[r * S + k], acc[r]);
       }
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float y = silu_precise(acc[r]);
-        cat[r * KC + H + n] = y;
-        if (tap_state != nullptr && r0 + r < B) tap_state[static_cast<size_t>(r0 + r) * Hd + n] = y;
-      }
+      for (int r = 0; r < R; ++r)
+        if (r0 + r < B) state_feat[static_cast<size_t>(r0 + r) * Hd + n] = silu_precise(acc[r]);
     }
   }
+  cluster_sync();
+  for (int i = tid; i < R * Hd; i += blockDim.x) {
+    const int r = i / Hd, c = i % Hd;
+    cat[r * KC + H + c] = r0 + r < B ? state_feat[static_cast<size_t>(r0 + r) * Hd + c] : 0.f;
+  }
   __syncthreads();
-  // ---- fusion.0: Linear(KC -> F) ----
+  // ---- fusion.0: Linear(KC -> F), this CTA's slice -> x1_scratch (global) ----
+  const int fper = ((F + HEAD_CL - 1) / HEAD_CL + NC - 1) / NC * NC;  // slice width, a multiple of NC
+  const int f_lo = crank * fper, f_hi = min(F, f_lo + fper);
   {
     const T* wf = static_cast<const T*>(w.w_f0);
-    for (int n0 = warp * NC; n0 < F; n0 += nwarps * NC) {
+    for (int n0 = f_lo + warp * NC; n0 < f_hi; n0 += nwarps * NC) {
       float acc[NC][R];
-      const int nv = F - n0 < NC ? F - n0 : NC;
+      const int nv = f_hi - n0 < NC ? f_hi - n0 : NC;
       warp_dot_rows<T, R, NC>(wf + static_cast<size_t>(n0) * KC, KC, nv, cat, KC, KC, lane, acc);
       if (lane == 0) {
 #pragma unroll
         for (int j = 0; j < NC; ++j)
           if (j < nv) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) x1[r * F + n0 + j] = acc[j][r] + w.b_f0[n0 + j];
+            for (int r = 0; r < R; ++r)
+              if (r0 + r < B) x1_scratch[static_cast<size_t>(r0 + r) * F + n0 + j] = acc[j][r] + w.b_f0[n0 + j];
           }
       }
     }
   }
+  cluster_sync();
+  for (int i = tid; i < R * F; i += blockDim.x) {
+    const int r = i / F, c = i % F;
+    x1[r * F + c] = r0 + r < B ? x1_scratch[static_cast<size_t>(r0 + r) * F + c] : 0.f;
+  }
   __syncthreads();
-  // ---- fusion.1 LayerNorm + fusion.2 SiLU (in place) ----
+  // ---- fusion.1 LayerNorm + fusion.2 SiLU (in place, every CTA on the full rows) ----
   for (int r = warp; r < R; r += nwarps) {
     float s = 0.f;
     for (int i = lane; i < F; i += 32) s += x1[r * F + i];
@@ -146,32 +171,34 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
       x1[r * F + i] = silu_precise((x1[r * F + i] - mean) * rstd * w.ln_f_w[i] + w.ln_f_b[i]);
   }
   __syncthreads();
-  // ---- fusion.4: Linear(F -> F) + SiLU ----
+  // ---- fusion.4: Linear(F -> F) + SiLU, this CTA's slice -> fused (global) ----
   {
     const T* wf = static_cast<const T*>(w.w_f4);
-    for (int n0 = warp * NC; n0 < F; n0 += nwarps * NC) {
+    for (int n0 = f_lo + warp * NC; n0 < f_hi; n0 += nwarps * NC) {
       float acc[NC][R];
-      const int nv = F - n0 < NC ? F - n0 : NC;
+      const int nv = f_hi - n0 < NC ? f_hi - n0 : NC;
       warp_dot_rows<T, R, NC>(wf + static_cast<size_t>(n0) * F, F, nv, x1, F, F, lane, acc);
       if (lane == 0) {
 #pragma unroll
         for (int j = 0; j < NC; ++j)
           if (j < nv) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-              const float y = silu_precise(acc[j][r] + w.b_f4[n0 + j]);
-              x2[r * F + n0 + j] = y;
-              if (tap_fused != nullptr && r0 + r < B) tap_fused[static_cast<size_t>(r0 + r) * F + n0 + j] = y;
-            }
+            for (int r = 0; r < R; ++r)
+              if (r0 + r < B) fused[static_cast<size_t>(r0 + r) * F + n0 + j] = silu_precise(acc[j][r] + w.b_f4[n0 + j]);
           }
       }
     }
   }
+  cluster_sync();
+  for (int i = tid; i < R * F; i += blockDim.x) {
+    const int r = i / F, c = i % F;
+    x2[r * F + c] = r0 + r < B ? fused[static_cast<size_t>(r0 + r) * F + c] : 0.f;
+  }
   __syncthreads();
-  // ---- action_head: Linear(F -> A) ----
+  // ---- action_head: Linear(F -> A), output neurons dealt round-robin over the cluster's warps ----
   {
     const T* wa = static_cast<const T*>(w.w_act);
-    for (int n = warp; n < A; n += nwarps) {
+    for (int n = crank * nwarps + warp; n < A; n += HEAD_CL * nwarps) {
       float acc[1][R];
       warp_dot_rows<T, R, 1>(wa + static_cast<size_t>(n) * F, F, 1, x2, F, F, lane, acc);
       if (lane == 0) {
@@ -185,14 +212,17 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
 
 template <typename T>
 int launch_head(const HeadWeights& w, const float* pooled, const float* states, float* actions,
-                float* tap_state, float* tap_fused, int B, cudaStream_t stream) {
-  constexpr int R = 2;
+                float* state_feat, float* x1_scratch, float* fused, int B, cudaStream_t stream) {
+  constexpr int R = 4;
   auto kfn = action_head_kernel<T, R>;
   const size_t smem = sizeof(float) * (static_cast<size_t>(R) * (w.H + w.Hd + 2 * w.F + w.S));
   FVLA_REQUIRE(smem <= 220 * 1024, "action head: hidden sizes too large for one CTA");
-  FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-  kfn<<<ceil_div(B, R), 256, smem, stream>>>(w, pooled, states, actions, tap_state, tap_fused, B);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  kfn<<<HEAD_CL * ceil_div(B, R), 256, smem, stream>>>(w, pooled, states, actions, state_feat, x1_scratch, fused, B);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -200,14 +230,16 @@ int launch_head(const HeadWeights& w, const float* pooled, const float* states, 
 }  // namespace
 
 int action_head(int dtype, const HeadWeights& w, const float* pooled, const float* states,
-                float* actions, float* tap_state_feat, float* tap_fused, int B,
+                float* actions, float* state_feat, float* x1_scratch, float* fused, int B,
                 cudaStream_t stream) {
   FVLA_REQUIRE(B > 0, "action head: empty batch");
+  FVLA_REQUIRE(state_feat != nullptr && x1_scratch != nullptr && fused != nullptr,
+               "action head: the three [B, *] fp32 exchange rows are required");
   FVLA_REQUIRE((w.H + w.Hd) % 8 == 0 && w.F % 8 == 0 && w.H % 4 == 0,
                "action head: H+hidden_dim and fusion_dim must be multiples of 8");
   if (dtype == DT_F32)
-    return launch_head<float>(w, pooled, states, actions, tap_state_feat, tap_fused, B, stream);
-  return launch_head<__nv_bfloat16>(w, pooled, states, actions, tap_state_feat, tap_fused, B, stream);
+    return launch_head<float>(w, pooled, states, actions, state_feat, x1_scratch, fused, B, stream);
+  return launch_head<__nv_bfloat16>(w, pooled, states, actions, state_feat, x1_scratch, fused, B, stream);
 }
 
 }  // namespace fvla

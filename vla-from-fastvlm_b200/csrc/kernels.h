@@ -142,9 +142,11 @@ struct HeadWeights {  // all fp32 except the four matrices, which are in `dtype`
   const void* w_act; const float* b_act;           // action_head         [A, F]
   int H, S, Hd, F, A;
 };
-// pooled [B,H] fp32, states [B,S] fp32 -> actions [B,A] fp32; optional taps (fp32) may be null
+// pooled [B,H] fp32, states [B,S] fp32 -> actions [B,A] fp32.  state_feat [B,Hd], x1_scratch [B,F], fused [B,F]
+// (fp32) are the rows the kernel's CTA cluster exchanges layer outputs through; state_feat / fused are also the
+// parity taps.
 int action_head(int dtype, const HeadWeights& w, const float* pooled, const float* states,
-                float* actions, float* tap_state_feat, float* tap_fused, int B,
+                float* actions, float* state_feat, float* x1_scratch, float* fused, int B,
                 cudaStream_t stream);
 
 // ---- small utilities -------------------------------------------------------------------------
