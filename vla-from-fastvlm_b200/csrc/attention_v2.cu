@@ -61,7 +61,7 @@ __device__ __forceinline__ void stage_async(uint32_t dst, const __nv_bfloat16* s
 }
 
 template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (HD <= 32 ? 3 : (HD <= 64 ? 2 : 1)))
 flash_attn_v2_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                      const __nv_bfloat16* __restrict__ v, int ld, __nv_bfloat16* __restrict__ o, int ld_o,
                      int N, int heads_q, int heads_kv, float scale_log2e) {
