@@ -34,12 +34,12 @@ template <> __device__ __forceinline__ float ld_src<uint8_t>(const uint8_t* p) {
 
 template <typename TS, typename TD>
 __global__ void preprocess_kernel(const TS* __restrict__ src, TD* __restrict__ dst, PreGeom g) {
-  const long long total = static_cast<long long>(g.B) * g.S * g.S;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int x = static_cast<int>(idx % g.S);
-  const int y = static_cast<int>((idx / g.S) % g.S);
-  const int b = static_cast<int>(idx / (static_cast<long long>(g.S) * g.S));
+  // grid (ceil(S/256), S, B): no index division (the 64-bit / and % of a flat index cost more than the resampling)
+  const int x = static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int y = static_cast<int>(blockIdx.y);
+  const int b = static_cast<int>(blockIdx.z);
+  if (x >= g.S) return;
+  const size_t idx = (static_cast<size_t>(b) * g.S + y) * g.S + x;
   float out[3];
   const int ry = y - g.pad_top, rx = x - g.pad_left;
   if (ry < 0 || rx < 0 || ry >= g.rh || rx >= g.rw) {
@@ -117,11 +117,13 @@ stem_conv_kernel(const T* __restrict__ in, const float* __restrict__ w,
                  int Cout) {
   const int Ho = H / 2, Wo = W / 2;
   const int CV = Cout / 8, WG = (Wo + PX - 1) / PX;
-  const long long total = static_cast<long long>(B) * Ho * WG * CV;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // 32-bit index arithmetic (the launcher checks the range): four 64-bit divisions per thread cost more than the
+  // 3x3 stencil itself
+  const unsigned total = static_cast<unsigned>(B) * Ho * WG * CV;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cv = static_cast<int>(idx % CV);
-  long long t = idx / CV;
+  unsigned t = idx / CV;
   const int xg = static_cast<int>(t % WG); t /= WG;
   const int oy = static_cast<int>(t % Ho);
   const int b = static_cast<int>(t / Ho);
@@ -212,11 +214,13 @@ dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w,
               int Ho, int Wo, int act) {
   const int Cout = Cin * MULT;
   const int CV = Cout / 8, WG = (Wo + PX - 1) / PX;
-  const long long total = static_cast<long long>(B) * Ho * WG * CV;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // 32-bit index arithmetic (the launcher checks the range): four 64-bit divisions per thread cost more than the
+  // 3x3 stencil itself
+  const unsigned total = static_cast<unsigned>(B) * Ho * WG * CV;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cv = static_cast<int>(idx % CV);
-  long long t = idx / CV;
+  unsigned t = idx / CV;
   const int xg = static_cast<int>(t % WG); t /= WG;
   const int oy = static_cast<int>(t % Ho);
   const int b = static_cast<int>(t / Ho);
@@ -287,6 +291,7 @@ int launch_dwconv(const void* in, const float* w, const float* bias, void* out, 
       static_cast<long long>(B) * Ho * ((Wo + PX - 1) / PX) * (Cout / 8);
   const int threads = 256;
   const long long blocks = ceil_div_ll(total, threads);
+  FVLA_REQUIRE(total < (1ll << 32) - threads, "dwconv: too many work items for 32-bit indexing");
   dwconv_kernel<T, K, STRIDE, MULT, PX><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
       static_cast<const T*>(in), w, bias, static_cast<T*>(out), B, H, W, Cin, Ho, Wo, act);
   FVLA_CUDA_CHECK(cudaGetLastError());
@@ -426,9 +431,9 @@ int se_gelu_t(const void* x, void* out, int B, int HW, int C, int Cr, const floa
 
 template <typename TS, typename TD>
 int launch_pre(const PreprocessArgs& a, const PreGeom& g, cudaStream_t s) {
-  const long long total = static_cast<long long>(a.B) * a.S * a.S;
-  preprocess_kernel<TS, TD><<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, s>>>(
-      static_cast<const TS*>(a.src), static_cast<TD*>(a.dst), g);
+  FVLA_REQUIRE(a.S <= 65535 && a.B <= 65535, "preprocess: image side / batch exceed the launch grid");
+  dim3 grid(static_cast<unsigned>(ceil_div(a.S, 256)), static_cast<unsigned>(a.S), static_cast<unsigned>(a.B));
+  preprocess_kernel<TS, TD><<<grid, 256, 0, s>>>(static_cast<const TS*>(a.src), static_cast<TD*>(a.dst), g);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
