@@ -15,14 +15,19 @@
 namespace fvla {
 namespace {
 
-constexpr int TW = 64;   // output pixels per tile row
 constexpr int TH = 8;    // output rows per tile (= warps per CTA)
 constexpr int CB = 32;   // channels per tile (4 vectors of 8)
+// output pixels per tile row: 64 (8 per lane) for 7x7; 32 (4 per lane) for 3x3, whose light arithmetic wants
+// occupancy instead of register blocking — half the accumulators and staging registers give 3 CTAs per SM
+template <int K> constexpr int tile_w() { return K == 3 ? 32 : 64; }
 
 template <int K> struct TileGeom {
+  static constexpr int TW = tile_w<K>();
+  static constexpr int PXT = TW / 8;                    // output pixels per lane
   static constexpr int IW = TW + K - 1;                 // input columns incl. halo
   static constexpr int IH = TH + K - 1;
-  static constexpr int XP_RAW = IW + (IW >> 3) + 1;     // padded slots per (row, cvec) line
+  static constexpr int PSH = PXT == 8 ? 3 : 2;          // one padding slot per lane group: xi + (xi >> PSH)
+  static constexpr int XP_RAW = IW + (IW >> PSH) + 1;   // padded slots per (row, cvec) line
   static constexpr int XP = XP_RAW + ((2 - (XP_RAW & 7)) & 7);  // = 2 (mod 8)
   static constexpr int IN_BYTES = IH * 4 * XP * 16;
 };
@@ -63,11 +68,12 @@ __device__ __forceinline__ float2 h2_to_f2(uint32_t h) {
 }
 
 template <int K>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (K == 3 ? 3 : 2))
 dwconv_tiled_h_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W,
                       int C, int act) {
   using G = TileGeom<K>;
+  constexpr int TW = G::TW, PXT = G::PXT;
   constexpr int PAD = K / 2;
   extern __shared__ __align__(16) uint8_t smem_dw[];
   const uint32_t s_in = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dw));
@@ -113,7 +119,7 @@ dwconv_tiled_h_kernel(const __nv_bfloat16* __restrict__ in, const float* __restr
       const int cv = idx & 3;
       const int xi = (idx >> 2) % G::IW;
       const int r = (idx >> 2) / G::IW;
-      const uint32_t dst = s_in + static_cast<uint32_t>(((r * 4 + cv) * G::XP + xi + (xi >> 3)) * 16);
+      const uint32_t dst = s_in + static_cast<uint32_t>(((r * 4 + cv) * G::XP + xi + (xi >> G::PSH)) * 16);
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(bf16x2_to_f16x2_sat(stage[it].x)),
                    "r"(bf16x2_to_f16x2_sat(stage[it].y)), "r"(bf16x2_to_f16x2_sat(stage[it].z)),
                    "r"(bf16x2_to_f16x2_sat(stage[it].w))
@@ -125,17 +131,17 @@ dwconv_tiled_h_kernel(const __nv_bfloat16* __restrict__ in, const float* __restr
   // ---- compute: warp = output row, lane = (channel vector, 8-pixel group) ----
   const int row = tid >> 5, lane = tid & 31;
   const int cv = lane & 3, pg = lane >> 2;
-  float acc[8][8];
+  float acc[PXT][8];
   {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + cv * 8));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + cv * 8) + 1);
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
+    for (int o = 0; o < PXT; ++o) {
       acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
       acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
     }
   }
-  uint32_t racc[8][4];  // packed fp16 partial sums of up to two kernel rows
+  uint32_t racc[PXT][4];  // packed fp16 partial sums of up to two kernel rows
 #pragma unroll 1
   for (int ky = 0; ky < K; ++ky) {
     uint32_t wr[K][4];
@@ -147,14 +153,14 @@ dwconv_tiled_h_kernel(const __nv_bfloat16* __restrict__ in, const float* __restr
     const bool fresh = (ky & 1) == 0;  // first row of a pair: start the partial sums with a multiply
     const uint32_t line = s_in + static_cast<uint32_t>((((row + ky) * 4 + cv) * G::XP) * 16);
 #pragma unroll
-    for (int i = 0; i < 8 + K - 1; ++i) {
-      const int xi = pg * 8 + i;
+    for (int i = 0; i < PXT + K - 1; ++i) {
+      const int xi = pg * PXT + i;
       uint32_t x[4];
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                    : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
-                   : "r"(line + static_cast<uint32_t>((xi + (xi >> 3)) * 16)));
+                   : "r"(line + static_cast<uint32_t>((xi + (xi >> G::PSH)) * 16)));
 #pragma unroll
-      for (int o = 0; o < 8; ++o) {
+      for (int o = 0; o < PXT; ++o) {
         const int kx = i - o;
         if (kx < 0 || kx >= K) continue;
         if (kx == 0 && fresh) {
@@ -168,7 +174,7 @@ dwconv_tiled_h_kernel(const __nv_bfloat16* __restrict__ in, const float* __restr
     }
     if (!fresh || ky == K - 1) {  // flush the pair into the fp32 accumulators
 #pragma unroll
-      for (int o = 0; o < 8; ++o)
+      for (int o = 0; o < PXT; ++o)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float2 f = h2_to_f2(racc[o][c]);
@@ -179,9 +185,9 @@ dwconv_tiled_h_kernel(const __nv_bfloat16* __restrict__ in, const float* __restr
   }
   // ---- store ----
   __nv_bfloat16* orow =
-      out + ((static_cast<size_t>(b) * H + (y0 + row)) * W + x0 + pg * 8) * C + c0 + cv * 8;
+      out + ((static_cast<size_t>(b) * H + (y0 + row)) * W + x0 + pg * PXT) * C + c0 + cv * 8;
 #pragma unroll
-  for (int o = 0; o < 8; ++o) {
+  for (int o = 0; o < PXT; ++o) {
     Vec8<__nv_bfloat16> r;
 #pragma unroll
     for (int c = 0; c < 8; ++c) r.v[c] = acc[o][c];
@@ -204,7 +210,7 @@ int launch_tiled_h(const void* in, const float* w, const float* bias, void* out,
     FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  dim3 grid((W / TW) * (H / TH), C / CB, B);
+  dim3 grid((W / G::TW) * (H / TH), C / CB, B);
   kfn<<<grid, 256, SMEM, stream>>>(static_cast<const __nv_bfloat16*>(in), w, bias,
                                    static_cast<__nv_bfloat16*>(out), H, W, C, act);
   FVLA_CUDA_CHECK(cudaGetLastError());
@@ -355,7 +361,7 @@ dwconv7_s2m2_tiled_kernel(const __nv_bfloat16* __restrict__ in, const float* __r
 }  // namespace
 
 bool dwconv_tiled_supported(int dtype, int H, int W, int C, int mult, int k, int stride) {
-  return dtype == DT_BF16 && stride == 1 && mult == 1 && (k == 3 || k == 7) && W % TW == 0 &&
+  return dtype == DT_BF16 && stride == 1 && mult == 1 && (k == 3 || k == 7) && W % 64 == 0 &&
          H % TH == 0 && C % CB == 0;
 }
 
