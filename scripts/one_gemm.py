@@ -8,11 +8,12 @@ import torch  # noqa: E402
 from vla_fastvlm import _native as N  # noqa: E402
 
 M, Nn, K = (int(x) for x in sys.argv[1:4])
-act = 1 if len(sys.argv) > 4 and sys.argv[4] == "gelu" else 0
+mode = sys.argv[4] if len(sys.argv) > 4 else ""
+act = {"gelu": 1, "gelu16": 5}.get(mode, 0)
 a = torch.randn(M, K, device="cuda").bfloat16()
 w = (torch.randn(Nn, K, device="cuda") / K ** 0.5).bfloat16()
 bias = torch.randn(Nn, device="cuda")
-out = torch.empty(M, Nn, device="cuda", dtype=torch.bfloat16)
+out = torch.empty(M, Nn, device="cuda", dtype=torch.float16 if act == 5 else torch.bfloat16)
 for _ in range(3):
     N.op_gemm(a, w, bias=bias, act=act, out=out)
 torch.cuda.synchronize()

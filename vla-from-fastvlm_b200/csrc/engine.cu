@@ -313,6 +313,19 @@ int Engine::pack_vision() {
       for (int o = 0; o < d0; ++o)
         for (int t = 0; t < 27; ++t) wg[static_cast<size_t>(o) * 32 + t] = packed[static_cast<size_t>(t) * d0 + o];
       if (int rc = make_gemm(&stem0_gemm_, wg, d0, 32, &b->data, true)) return rc;
+      if (stem_fused_supported(cfg.dtype, cfg.image_size, d0)) {
+        std::vector<uint32_t> tab(stem_fused_btab_words(d0));
+        stem_fused_build_btab(packed.data(), d0, tab.data());
+        void* p = nullptr;
+        FVLA_CUDA_CHECK(cudaMalloc(&p, tab.size() * 4));
+        FVLA_CUDA_CHECK(cudaMemcpy(p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        dev_allocs_.push_back(p);
+        stem_btab_ = static_cast<uint32_t*>(p);
+        std::vector<float> bh(b->data);
+        for (auto& v : bh) v *= 0.5f;
+        stem0_bh_ = upload_f32(bh);
+        FVLA_REQUIRE(stem0_bh_ != nullptr, "cudaMalloc failed (stem bias)");
+      }
     }
   }
   if (int rc = need(S(kVis, "patch_embed.1.reparam_conv.weight"), &w, {d0, 1, 3, 3})) return rc;
@@ -816,26 +829,39 @@ int Engine::vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats
 
   // ---- stem ----
   const int d0 = cfg.vis_dims[0];
-  if (cfg.dtype == FVLA_BF16) {
-    // 27-tap patches -> [M, 32] bf16, then a K=32 tensor-core GEMM with bias + GELU in the epilogue
-    char* col = static_cast<char*>(ws_.bufs["vis_col"].first);
-    const int Ms = bc * (S / 2) * (S / 2);
+  static const bool fuse_stem = std::getenv("FVLA_DISABLE_FUSED_STEM") == nullptr;  // A/B switch for profiling
+  if (fuse_stem && stem_btab_ != nullptr) {
+    // stem.0 (tensor cores, implicit GEMM) + GELU + stem.1 (depthwise 3x3 s2) + GELU in one kernel
     ++launches;
+    const double fl = 2.0 * 27 * static_cast<double>(bc) * (S / 2) * (S / 2) * d0 +
+                      2.0 * 9 * static_cast<double>(bc) * (S / 4) * (S / 4) * d0;
+    flops += fl;
     prof_begin(s);
-    if (int rc = stem_im2col_bf16(pre, col, bc, S, S, s)) return rc;
-    prof_end("vis.stem_im2col", 0.0, static_cast<double>(bc) * e * (static_cast<double>(S) * S * 4 + static_cast<double>(Ms / bc) * 32), s);
-    const double before = flops;
-    if (int rc = run_gemm(stem0_gemm_, col, Hb, Ms, ACT_GELU, nullptr, false, s)) return rc;
-    flops = before + 2.0 * 27 * static_cast<double>(Ms) * d0;  // algorithmic taps, not the zero padding
+    if (int rc = stem_fused(pre, stem_btab_, stem0_bh_, stem1_.w, stem1_.bias, Z, bc, S, d0, s)) return rc;
+    prof_end("vis.stem_fused", fl,
+             static_cast<double>(bc) * e * (static_cast<double>(S) * S * 4 + static_cast<double>(S / 4) * (S / 4) * d0), s);
   } else {
-    ++launches;
-    flops += 2.0 * 27 * static_cast<double>(bc) * (S / 2) * (S / 2) * d0;
-    prof_begin(s);
-    if (int rc = stem_conv3x3_s2(cfg.dtype, pre, stem0_w_, stem0_b_, Hb, bc, S, S, d0, s)) return rc;
-    prof_end("vis.stem_conv3x3", 2.0 * 27 * static_cast<double>(bc) * (S / 2) * (S / 2) * d0,
-             static_cast<double>(bc) * e * (static_cast<double>(S) * S * 4 + static_cast<double>(S / 2) * (S / 2) * d0), s);
+    if (cfg.dtype == FVLA_BF16) {
+      // 27-tap patches -> [M, 32] bf16, then a K=32 tensor-core GEMM with bias + GELU in the epilogue
+      char* col = static_cast<char*>(ws_.bufs["vis_col"].first);
+      const int Ms = bc * (S / 2) * (S / 2);
+      ++launches;
+      prof_begin(s);
+      if (int rc = stem_im2col_bf16(pre, col, bc, S, S, s)) return rc;
+      prof_end("vis.stem_im2col", 0.0, static_cast<double>(bc) * e * (static_cast<double>(S) * S * 4 + static_cast<double>(Ms / bc) * 32), s);
+      const double before = flops;
+      if (int rc = run_gemm(stem0_gemm_, col, Hb, Ms, ACT_GELU, nullptr, false, s)) return rc;
+      flops = before + 2.0 * 27 * static_cast<double>(Ms) * d0;  // algorithmic taps, not the zero padding
+    } else {
+      ++launches;
+      flops += 2.0 * 27 * static_cast<double>(bc) * (S / 2) * (S / 2) * d0;
+      prof_begin(s);
+      if (int rc = stem_conv3x3_s2(cfg.dtype, pre, stem0_w_, stem0_b_, Hb, bc, S, S, d0, s)) return rc;
+      prof_end("vis.stem_conv3x3", 2.0 * 27 * static_cast<double>(bc) * (S / 2) * (S / 2) * d0,
+               static_cast<double>(bc) * e * (static_cast<double>(S) * S * 4 + static_cast<double>(S / 2) * (S / 2) * d0), s);
+    }
+    if (int rc = run_dw(stem1_, Hb, Z, bc, S / 2, S / 2, s)) return rc;
   }
-  if (int rc = run_dw(stem1_, Hb, Z, bc, S / 2, S / 2, s)) return rc;
   int side = S / 4;
   if (int rc = run_gemm(stem2_, Z, X, bc * side * side, ACT_GELU, nullptr, false, s)) return rc;
   if (int rc = tap(FVLA_TAP_STEM, X, static_cast<size_t>(bc) * side * side * d0 * e,

@@ -117,6 +117,7 @@ class Engine {
 
   // packed model
   float* stem0_w_ = nullptr; float* stem0_b_ = nullptr;
+  uint32_t* stem_btab_ = nullptr; float* stem0_bh_ = nullptr;  // fused stem: B-fragment table, halved bias
   GemmW stem0_gemm_;  // bf16 mode: im2col form [d0][32]
   DwW stem1_; GemmW stem2_;
   std::vector<VisStage> stages_;

@@ -68,6 +68,13 @@ int stem_conv3x3_s2(int dtype, const void* in, const float* w_packed, const floa
                     int B, int H, int W, int Cout, cudaStream_t stream);
 // bf16 tensor-core route for the same conv: gather 27-tap patches into [B*(H/2)*(W/2), 32] (cols 27..31 zero)
 int stem_im2col_bf16(const void* in, void* col, int B, int H, int W, cudaStream_t stream);
+// stem.0 + stem.1 fused (bf16): [B,S,S,4] -> GELU(dw3x3 s2(GELU(conv3x3 s2 + b0)) + b1) -> [B,S/4,S/4,C]; the
+// S/2-sided intermediate map stays in shared memory (stem_fused.cu).  btab from stem_fused_build_btab (host).
+bool stem_fused_supported(int dtype, int S, int C);
+size_t stem_fused_btab_words(int C);
+void stem_fused_build_btab(const float* w0_packed, int C, uint32_t* btab_host);
+int stem_fused(const void* in, const uint32_t* btab, const float* b0_half, const float* w1_packed, const float* b1,
+               void* out, int B, int S, int C, cudaStream_t stream);
 // Depthwise / grouped k x k conv, groups = Cin, Cout = mult*Cin (mult 1 or 2), pad k/2,
 // + bias (+ GELU).  w_packed: [k*k][Cout] fp32.
 // `wtab` (optional): the tensor-core 7x7 path's Toeplitz table from dwconv7_mma_prepare(); built on the
