@@ -354,13 +354,14 @@ se_fc1_kernel(const float* __restrict__ mean, const float* __restrict__ w1, cons
   constexpr int MAXV = 16;  // C <= 32 * MAXV * ... handled by the strided loop below
   const int r = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int b_lo = blockIdx.y * nw;  // grid.y slices the batch: one sample per warp
   const float* wr = w1 + static_cast<size_t>(r) * C;
   float wreg[MAXV * 8];
   const int nv = (C + 31) / 32;  // elements per lane (<= 128)
 #pragma unroll
   for (int i = 0; i < MAXV * 8; ++i) wreg[i] = (i < nv && lane + 32 * i < C) ? __ldg(wr + lane + 32 * i) : 0.f;
   const float bias = b1[r];
-  for (int b = warp; b < B; b += nw) {
+  for (int b = b_lo + warp; b < min(B, b_lo + nw); b += nw) {
     const float* m = mean + static_cast<size_t>(b) * C;
     float a = 0.f;
 #pragma unroll
@@ -420,7 +421,7 @@ int se_gelu_t(const void* x, void* out, int B, int HW, int C, int Cr, const floa
   FVLA_REQUIRE(C <= 4096 && Cr <= 256 && Cr <= C, "se_gelu: channel counts out of range");
   float* hidden = gate;
   float* gates = mean;
-  se_fc1_kernel<<<Cr, 256, 0, s>>>(mean, w1, b1, hidden, B, C, Cr);
+  se_fc1_kernel<<<dim3(Cr, ceil_div(B, 8)), 256, 0, s>>>(mean, w1, b1, hidden, B, C, Cr);
   se_fc2_kernel<<<ceil_div(C, 8), 256, 0, s>>>(hidden, w2, b2, gates, B, C, Cr);
   const long long tv = static_cast<long long>(B) * HW * (C / 8);
   se_scale_gelu_kernel<T><<<static_cast<unsigned>(ceil_div_ll(tv, 256)), 256, 0, s>>>(

@@ -243,7 +243,7 @@ __device__ __forceinline__ uint32_t dup_hi(uint32_t v) {
   return r;
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 dwconv7_s2m2_tiled_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W,
                           int Cin, int act) {
