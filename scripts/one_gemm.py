@@ -10,11 +10,13 @@ from vla_fastvlm import _native as N  # noqa: E402
 M, Nn, K = (int(x) for x in sys.argv[1:4])
 mode = sys.argv[4] if len(sys.argv) > 4 else ""
 act = {"gelu": 1, "gelu16": 5}.get(mode, 0)
+use_res = mode == "res"
 a = torch.randn(M, K, device="cuda").bfloat16()
 w = (torch.randn(Nn, K, device="cuda") / K ** 0.5).bfloat16()
 bias = torch.randn(Nn, device="cuda")
 out = torch.empty(M, Nn, device="cuda", dtype=torch.float16 if act == 5 else torch.bfloat16)
+res = torch.randn(M, Nn, device="cuda").bfloat16() if use_res else None
 for _ in range(3):
-    N.op_gemm(a, w, bias=bias, act=act, out=out)
+    N.op_gemm(a, w, bias=bias, act=act, resid=res, out=out)
 torch.cuda.synchronize()
 print("ok", float(out.float().abs().mean()))

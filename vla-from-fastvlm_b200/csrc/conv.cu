@@ -7,6 +7,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace fvla {
 namespace {
 
@@ -495,7 +497,8 @@ int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, 
            int H, int W, int Cin, int mult, int ksize, int stride, int act, cudaStream_t stream,
            const uint32_t* wtab) {
   FVLA_REQUIRE((Cin * mult) % 8 == 0, "dwconv: output channels must be a multiple of 8");
-  if (dwconv7_mma_supported(dtype, H, W, Cin, mult, ksize, stride, act)) {
+  static const bool mma_on = std::getenv("FVLA_DISABLE_DWCONV_MMA") == nullptr;  // A/B switch (precision / profiling)
+  if (mma_on && dwconv7_mma_supported(dtype, H, W, Cin, mult, ksize, stride, act)) {
     if (wtab == nullptr) {
       // op-level callers (tests, micro-benchmarks) pass only the fp32 taps: build the table into a scratch
       // buffer on the same stream (the engine builds its tables once at finalize)
@@ -515,7 +518,8 @@ int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, 
   }
   if (dwconv_s2m2_tiled_supported(dtype, H, W, Cin, mult, ksize, stride) && (act == ACT_NONE || act == ACT_GELU))
     return dwconv_s2m2_tiled(in, w_packed, bias, out, B, H, W, Cin, act, stream);
-  if (dwconv_tiled_supported(dtype, H, W, Cin, mult, ksize, stride))
+  static const bool tiled_on = std::getenv("FVLA_DISABLE_DWCONV_TILED") == nullptr;  // A/B switch (precision / profiling)
+  if (tiled_on && dwconv_tiled_supported(dtype, H, W, Cin, mult, ksize, stride))
     return dwconv_tiled(in, w_packed, bias, out, B, H, W, Cin, ksize, act, stream);
   if (dtype == DT_F32)
     return dwconv_dispatch<float>(in, w_packed, bias, out, B, H, W, Cin, mult, ksize, stride, act, stream);
