@@ -95,3 +95,38 @@ def test_plugin_select_action_and_forward():
         pred = pol._predict_actions(batch)
     pre, post = make_fastvla_pre_post_processors(cfg, dataset_stats=None)
     assert post(pred).device.type == "cpu"
+
+
+def test_training_step_updates_head_and_engine():
+    """The data-parallel training step (world size 1 here): frozen backbone in the engine, head through autograd,
+    gradients accumulated into the flat all-reduce buffer, AdamW on the head only — the loss falls, the backbone's
+    tensors never get gradients, and eval-mode inference (fused head kernel) sees the updated head."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from vla_fastvlm.lerobot_fastvla import FastVLAConfig, FastVLAPolicy
+    from vla_fastvlm.training import HeadGradAllReduce, train_step
+
+    inp, outp = _features(n_cam=1)
+    cfg = FastVLAConfig(input_features=inp, output_features=outp, device="cuda", vlm_model_name="synthetic:tiny",
+                        hidden_dim=TINY_HEAD["hidden_dim"], fusion_dim=TINY_HEAD["fusion_dim"], image_token_mode="prefix",
+                        dropout=0.0)
+    pol = FastVLAPolicy(cfg).cuda()
+    g = torch.Generator().manual_seed(3)
+    B = 4
+    batch = {"observation.images.cam0": torch.rand(B, 3, 96, 128, generator=g).cuda(),
+             "observation.state": torch.randn(B, 6, generator=g).cuda(), "task": ["push the block"] * B,
+             "action": torch.randn(B, 1, 5, generator=g).cuda()}
+    before = pol.select_action(batch).clone()
+    pol.reset()
+    trainable = [p for p in pol.get_optim_params() if p.requires_grad]
+    red = HeadGradAllReduce(trainable)
+    assert red.numel == sum(p.numel() for p in trainable) and red.world_size == 1
+    opt = torch.optim.AdamW(trainable, lr=3e-3, weight_decay=0.0)
+    losses = [train_step(pol, batch, opt, red)[0] for _ in range(12)]
+    assert losses[-1] < 0.7 * losses[0], losses
+    after = pol.select_action(batch)
+    assert not torch.allclose(after, before)                                  # the engine picked up the new head
+    pol.train()
+    with torch.no_grad():
+        ref = pol._predict_actions(batch)                                     # autograd-path head on engine features
+    assert torch.allclose(after, ref, atol=2e-2, rtol=2e-2)
