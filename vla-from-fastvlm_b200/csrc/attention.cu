@@ -352,7 +352,7 @@ int attention(int dtype, const AttnArgs& a, cudaStream_t stream) {
   if (int rc = check_attn(a)) return rc;
   if (dtype == DT_F32) return launch_simt<float>(a, stream);
   // short causal prefills (T' = 272: three 128-row blocks, the last one nearly empty) keep the 64-query kernel
-  if (attention_v2_supported(a) && !(a.causal && a.N < 512)) return attention_v2(a, stream);
+  if (attention_v2_supported(a)) return attention_v2(a, stream);
   const bool rope = a.rope_cos != nullptr;
   if (a.head_dim == 32 && !a.causal && !rope) return launch_flash<32, false, false>(a, stream);
   if (a.head_dim == 64 && a.causal && rope) return launch_flash<64, true, true>(a, stream);

@@ -14,7 +14,6 @@
 namespace fvla {
 namespace {
 
-constexpr int BQ2 = 128;
 constexpr int BKV2 = 64;
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -60,11 +59,14 @@ __device__ __forceinline__ void stage_async(uint32_t dst, const __nv_bfloat16* s
   }
 }
 
-template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(256, (HD <= 32 ? 3 : (HD <= 64 ? 2 : 1)))
+// NWARPS x 16 queries per CTA: 8 warps for long sequences (K/V tiles staged half as often per query), 4 warps for
+// the short causal Qwen2 prefill (T' = 272: 128-query CTAs would leave 29 % of their rows empty)
+template <int HD, bool CAUSAL, int NWARPS>
+__global__ void __launch_bounds__(32 * NWARPS, (NWARPS == 8 ? (HD <= 32 ? 3 : (HD <= 64 ? 2 : 1)) : (HD <= 64 ? 4 : 2)))
 flash_attn_v2_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                      const __nv_bfloat16* __restrict__ v, int ld, __nv_bfloat16* __restrict__ o, int ld_o,
                      int N, int heads_q, int heads_kv, float scale_log2e) {
+  constexpr int BQ2 = 16 * NWARPS, NT = 32 * NWARPS;
   constexpr int LDS = HD + 8;          // elements
   constexpr int LDSB = LDS * 2;        // bytes
   constexpr int KV_TILE_B = BKV2 * LDSB;
@@ -86,9 +88,9 @@ flash_attn_v2_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   int kv_blocks = (N + BKV2 - 1) / BKV2;
   if (CAUSAL) kv_blocks = min(kv_blocks, (q0 + BQ2 + BKV2 - 1) / BKV2);
 
-  stage_async<HD, BQ2, 256>(sQ, qp, ld, q0, N);
-  stage_async<HD, BKV2, 256>(sK, kp, ld, 0, N);
-  stage_async<HD, BKV2, 256>(sV, vp, ld, 0, N);
+  stage_async<HD, BQ2, NT>(sQ, qp, ld, q0, N);
+  stage_async<HD, BKV2, NT>(sK, kp, ld, 0, N);
+  stage_async<HD, BKV2, NT>(sV, vp, ld, 0, N);
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -112,8 +114,8 @@ flash_attn_v2_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   for (int kb = 0; kb < kv_blocks; ++kb) {
     const int st = kb & 1;
     if (kb + 1 < kv_blocks) {  // prefetch the next tile into the other stage
-      stage_async<HD, BKV2, 256>(sK + (st ^ 1) * KV_TILE_B, kp, ld, (kb + 1) * BKV2, N);
-      stage_async<HD, BKV2, 256>(sV + (st ^ 1) * KV_TILE_B, vp, ld, (kb + 1) * BKV2, N);
+      stage_async<HD, BKV2, NT>(sK + (st ^ 1) * KV_TILE_B, kp, ld, (kb + 1) * BKV2, N);
+      stage_async<HD, BKV2, NT>(sV + (st ^ 1) * KV_TILE_B, vp, ld, (kb + 1) * BKV2, N);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 
@@ -232,9 +234,10 @@ flash_attn_v2_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   }
 }
 
-template <int HD, bool CAUSAL>
+template <int HD, bool CAUSAL, int NWARPS>
 int launch_v2(const AttnArgs& a, cudaStream_t stream) {
-  auto kfn = flash_attn_v2_kernel<HD, CAUSAL>;
+  auto kfn = flash_attn_v2_kernel<HD, CAUSAL, NWARPS>;
+  constexpr int BQ2 = 16 * NWARPS;
   constexpr int SMEM = (BQ2 + 4 * BKV2) * (HD + 8) * 2;
   static bool attr_set = false;
   if (!attr_set) {
@@ -242,7 +245,7 @@ int launch_v2(const AttnArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid(ceil_div(a.N, BQ2), a.heads_q, a.B);
-  kfn<<<grid, 256, SMEM, stream>>>(static_cast<const __nv_bfloat16*>(a.q), static_cast<const __nv_bfloat16*>(a.k),
+  kfn<<<grid, 32 * NWARPS, SMEM, stream>>>(static_cast<const __nv_bfloat16*>(a.q), static_cast<const __nv_bfloat16*>(a.k),
                                    static_cast<const __nv_bfloat16*>(a.v), a.ld_qkv,
                                    static_cast<__nv_bfloat16*>(a.o), a.ld_o, a.N, a.heads_q, a.heads_kv,
                                    a.scale * 1.4426950408889634f);
@@ -257,9 +260,17 @@ bool attention_v2_supported(const AttnArgs& a) {
 }
 
 int attention_v2(const AttnArgs& a, cudaStream_t stream) {
-  if (a.head_dim == 32) return a.causal ? launch_v2<32, true>(a, stream) : launch_v2<32, false>(a, stream);
-  if (a.head_dim == 64) return a.causal ? launch_v2<64, true>(a, stream) : launch_v2<64, false>(a, stream);
-  return a.causal ? launch_v2<128, true>(a, stream) : launch_v2<128, false>(a, stream);
+  const bool small = a.causal && a.N < 512;  // the short causal prefill: 64-query CTAs
+  if (a.head_dim == 32) {
+    if (small) return a.causal ? launch_v2<32, true, 4>(a, stream) : launch_v2<32, false, 4>(a, stream);
+    return a.causal ? launch_v2<32, true, 8>(a, stream) : launch_v2<32, false, 8>(a, stream);
+  }
+  if (a.head_dim == 64) {
+    if (small) return a.causal ? launch_v2<64, true, 4>(a, stream) : launch_v2<64, false, 4>(a, stream);
+    return a.causal ? launch_v2<64, true, 8>(a, stream) : launch_v2<64, false, 8>(a, stream);
+  }
+  if (small) return a.causal ? launch_v2<128, true, 4>(a, stream) : launch_v2<128, false, 4>(a, stream);
+  return a.causal ? launch_v2<128, true, 8>(a, stream) : launch_v2<128, false, 8>(a, stream);
 }
 
 }  // namespace fvla
