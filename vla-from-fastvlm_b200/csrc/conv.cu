@@ -34,65 +34,91 @@ template <> __device__ __forceinline__ float ld_src<uint8_t>(const uint8_t* p) {
   return static_cast<float>(*p);
 }
 
+// One thread = PRE_PX consecutive output pixels of one row: the row's vertical interpolation set-up (source rows,
+// weights, base pointers) is computed once, and neighbouring outputs re-read the same source texels from L1.
+constexpr int PRE_PX = 4;
+
 template <typename TS, typename TD>
-__global__ void preprocess_kernel(const TS* __restrict__ src, TD* __restrict__ dst, PreGeom g) {
-  // grid (ceil(S/256), S, B): no index division (the 64-bit / and % of a flat index cost more than the resampling)
-  const int x = static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+preprocess_kernel(const TS* __restrict__ src, TD* __restrict__ dst, PreGeom g) {
+  // grid (ceil(S / (128 * PRE_PX)), S, B): no index division
+  const int xb = (static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x) * PRE_PX;
   const int y = static_cast<int>(blockIdx.y);
   const int b = static_cast<int>(blockIdx.z);
-  if (x >= g.S) return;
-  const size_t idx = (static_cast<size_t>(b) * g.S + y) * g.S + x;
-  float out[3];
-  const int ry = y - g.pad_top, rx = x - g.pad_left;
-  if (ry < 0 || rx < 0 || ry >= g.rh || rx >= g.rw) {
-    out[0] = out[1] = out[2] = g.pad_value;
-  } else {
+  if (xb >= g.S) return;
+  const int ry = y - g.pad_top;
+  const bool row_in = ry >= 0 && ry < g.rh;
+  int y0 = 0, y1 = 0;
+  float ly = 0.f, hy = 1.f;
+  if (row_in) {
     float fy = g.sy * (static_cast<float>(ry) + 0.5f) - 0.5f;
-    float fx = g.sx * (static_cast<float>(rx) + 0.5f) - 0.5f;
     fy = fy < 0.f ? 0.f : fy;
-    fx = fx < 0.f ? 0.f : fx;
-    int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    y0 = static_cast<int>(fy);
     y0 = y0 > g.h - 1 ? g.h - 1 : y0;
-    x0 = x0 > g.w - 1 ? g.w - 1 : x0;
-    const int y1 = y0 + (y0 < g.h - 1 ? 1 : 0), x1 = x0 + (x0 < g.w - 1 ? 1 : 0);
-    const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
-    const float hy = 1.f - ly, hx = 1.f - lx;
+    y1 = y0 + (y0 < g.h - 1 ? 1 : 0);
+    ly = fy - static_cast<float>(y0);
+    hy = 1.f - ly;
+  }
+  const size_t plane = static_cast<size_t>(g.h) * g.w;
+  const TS* img = src + static_cast<size_t>(b) * plane * g.C;
+  const size_t pix = g.nhwc ? static_cast<size_t>(g.C) : 1;          // element stride between neighbouring texels
+  const size_t row0 = static_cast<size_t>(y0) * g.w * pix, row1 = static_cast<size_t>(y1) * g.w * pix;
+  float out[PRE_PX][3];
+#pragma unroll
+  for (int i = 0; i < PRE_PX; ++i) {
+    const int x = xb + i;
+    const int rx = x - g.pad_left;
+    if (!row_in || rx < 0 || rx >= g.rw || x >= g.S) {
+      out[i][0] = out[i][1] = out[i][2] = g.pad_value;
+    } else {
+      float fx = g.sx * (static_cast<float>(rx) + 0.5f) - 0.5f;
+      fx = fx < 0.f ? 0.f : fx;
+      int x0 = static_cast<int>(fx);
+      x0 = x0 > g.w - 1 ? g.w - 1 : x0;
+      const int x1 = x0 + (x0 < g.w - 1 ? 1 : 0);
+      const float lx = fx - static_cast<float>(x0);
+      const float hx = 1.f - lx;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int cs = g.C == 1 ? 0 : c;  // grey -> replicate; >3 channels -> first three
+        const TS* base = img + (g.nhwc ? static_cast<size_t>(cs) : static_cast<size_t>(cs) * plane);
+        const float v00 = ld_src(base + row0 + static_cast<size_t>(x0) * pix);
+        const float v01 = ld_src(base + row0 + static_cast<size_t>(x1) * pix);
+        const float v10 = ld_src(base + row1 + static_cast<size_t>(x0) * pix);
+        const float v11 = ld_src(base + row1 + static_cast<size_t>(x1) * pix);
+        out[i][c] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+      }
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const int cs = g.C == 1 ? 0 : c;  // grey -> replicate; >3 channels -> first three
-      float v00, v01, v10, v11;
-      if (g.nhwc) {
-        const TS* base = src + (static_cast<size_t>(b) * g.h * g.w) * g.C + cs;
-        v00 = ld_src(base + (static_cast<size_t>(y0) * g.w + x0) * g.C);
-        v01 = ld_src(base + (static_cast<size_t>(y0) * g.w + x1) * g.C);
-        v10 = ld_src(base + (static_cast<size_t>(y1) * g.w + x0) * g.C);
-        v11 = ld_src(base + (static_cast<size_t>(y1) * g.w + x1) * g.C);
-      } else {
-        const TS* base = src + (static_cast<size_t>(b) * g.C + cs) * g.h * g.w;
-        v00 = ld_src(base + static_cast<size_t>(y0) * g.w + x0);
-        v01 = ld_src(base + static_cast<size_t>(y0) * g.w + x1);
-        v10 = ld_src(base + static_cast<size_t>(y1) * g.w + x0);
-        v11 = ld_src(base + static_cast<size_t>(y1) * g.w + x1);
-      }
-      out[c] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+      float v = out[i][c] * g.scale;
+      if (g.normalize) v = (v - g.mean[c]) * g.inv_std[c];
+      out[i][c] = v;
     }
   }
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float v = out[c] * g.scale;
-    if (g.normalize) v = (v - g.mean[c]) * g.inv_std[c];
-    out[c] = v;
-  }
+  const size_t idx = (static_cast<size_t>(b) * g.S + y) * g.S + xb;
   TD* d = dst + idx * 4;
   if constexpr (sizeof(TD) == 4) {
-    *reinterpret_cast<float4*>(d) = make_float4(out[0], out[1], out[2], 0.f);
+#pragma unroll
+    for (int i = 0; i < PRE_PX; ++i)
+      if (xb + i < g.S) reinterpret_cast<float4*>(d)[i] = make_float4(out[i][0], out[i][1], out[i][2], 0.f);
   } else {
-    __nv_bfloat162 a = __floats2bfloat162_rn(out[0], out[1]);
-    __nv_bfloat162 c = __floats2bfloat162_rn(out[2], 0.f);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&a);
-    pk.y = *reinterpret_cast<uint32_t*>(&c);
-    *reinterpret_cast<uint2*>(d) = pk;
+    uint32_t w[2 * PRE_PX];
+#pragma unroll
+    for (int i = 0; i < PRE_PX; ++i) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(out[i][0], out[i][1]);
+      __nv_bfloat162 c = __floats2bfloat162_rn(out[i][2], 0.f);
+      w[2 * i] = *reinterpret_cast<uint32_t*>(&a);
+      w[2 * i + 1] = *reinterpret_cast<uint32_t*>(&c);
+    }
+    if (xb + PRE_PX <= g.S) {  // 32 contiguous bytes
+      reinterpret_cast<uint4*>(d)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      reinterpret_cast<uint4*>(d)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < PRE_PX; ++i)
+        if (xb + i < g.S) reinterpret_cast<uint2*>(d)[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+    }
   }
 }
 
@@ -435,8 +461,8 @@ int se_gelu_t(const void* x, void* out, int B, int HW, int C, int Cr, const floa
 template <typename TS, typename TD>
 int launch_pre(const PreprocessArgs& a, const PreGeom& g, cudaStream_t s) {
   FVLA_REQUIRE(a.S <= 65535 && a.B <= 65535, "preprocess: image side / batch exceed the launch grid");
-  dim3 grid(static_cast<unsigned>(ceil_div(a.S, 256)), static_cast<unsigned>(a.S), static_cast<unsigned>(a.B));
-  preprocess_kernel<TS, TD><<<grid, 256, 0, s>>>(static_cast<const TS*>(a.src), static_cast<TD*>(a.dst), g);
+  dim3 grid(static_cast<unsigned>(ceil_div(a.S, 128 * PRE_PX)), static_cast<unsigned>(a.S), static_cast<unsigned>(a.B));
+  preprocess_kernel<TS, TD><<<grid, 128, 0, s>>>(static_cast<const TS*>(a.src), static_cast<TD*>(a.dst), g);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
