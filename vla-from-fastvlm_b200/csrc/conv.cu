@@ -372,32 +372,37 @@ se_mean_kernel(const T* __restrict__ x, float* __restrict__ mean, int HW, int C)
   }
 }
 
-// hidden[b][r] = relu(W1[r] . mean[b] + b1[r]): one block per reduced channel r, the 3072-wide weight row held in
-// registers, warps striding over the samples (coalesced reads on both operands).  The previous one-block-per-sample
-// kernel streamed both weight matrices (4.7 MB) through every block with a stride-Cr access on W2: 0.53 ms at any
-// batch size, 8 % of the b=1 forward.
+// hidden[b][r] = relu(W1[r] . mean[b] + b1[r]).  The first version ran one block per sample and streamed both weight
+// matrices (4.7 MB) through every block with a stride-Cr access on W2: 0.53 ms at any batch size, 8 % of the b=1
+// forward; a version that cached the weight row in 128 registers per lane was occupancy-starved (0.29 ms).
 __global__ void __launch_bounds__(256)
 se_fc1_kernel(const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ b1,
               float* __restrict__ hidden, int B, int C, int Cr) {
-  constexpr int MAXV = 16;  // C <= 32 * MAXV * ... handled by the strided loop below
-  const int r = blockIdx.x;
+  // one warp per (reduced channel r, sample b): a 3072-long dot product as 128-bit loads, 4 in flight per operand
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int b_lo = blockIdx.y * nw;  // grid.y slices the batch: one sample per warp
-  const float* wr = w1 + static_cast<size_t>(r) * C;
-  float wreg[MAXV * 8];
-  const int nv = (C + 31) / 32;  // elements per lane (<= 128)
-#pragma unroll
-  for (int i = 0; i < MAXV * 8; ++i) wreg[i] = (i < nv && lane + 32 * i < C) ? __ldg(wr + lane + 32 * i) : 0.f;
-  const float bias = b1[r];
-  for (int b = b_lo + warp; b < min(B, b_lo + nw); b += nw) {
-    const float* m = mean + static_cast<size_t>(b) * C;
-    float a = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXV * 8; ++i)
-      if (i < nv && lane + 32 * i < C) a = fmaf(wreg[i], m[lane + 32 * i], a);
-    a = warp_sum(a);
-    if (lane == 0) hidden[static_cast<size_t>(b) * Cr + r] = fmaxf(a + bias, 0.f);
+  const int r = blockIdx.x;
+  const int b = blockIdx.y * nw + warp;
+  if (b >= B) return;
+  const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(r) * C);
+  const float4* m = reinterpret_cast<const float4*>(mean + static_cast<size_t>(b) * C);
+  const int n4 = C >> 2;  // C % 4 == 0 (checked by the launcher)
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int i = lane;
+  for (; i + 96 < n4; i += 128) {
+    const float4 w0 = __ldg(wr + i), w1v = __ldg(wr + i + 32), w2 = __ldg(wr + i + 64), w3 = __ldg(wr + i + 96);
+    const float4 x0 = m[i], x1 = m[i + 32], x2 = m[i + 64], x3 = m[i + 96];
+    a0 = fmaf(w0.x, x0.x, fmaf(w0.y, x0.y, fmaf(w0.z, x0.z, fmaf(w0.w, x0.w, a0))));
+    a1 = fmaf(w1v.x, x1.x, fmaf(w1v.y, x1.y, fmaf(w1v.z, x1.z, fmaf(w1v.w, x1.w, a1))));
+    a2 = fmaf(w2.x, x2.x, fmaf(w2.y, x2.y, fmaf(w2.z, x2.z, fmaf(w2.w, x2.w, a2))));
+    a3 = fmaf(w3.x, x3.x, fmaf(w3.y, x3.y, fmaf(w3.z, x3.z, fmaf(w3.w, x3.w, a3))));
   }
+  for (; i < n4; i += 32) {
+    const float4 w0 = __ldg(wr + i);
+    const float4 x0 = m[i];
+    a0 = fmaf(w0.x, x0.x, fmaf(w0.y, x0.y, fmaf(w0.z, x0.z, fmaf(w0.w, x0.w, a0))));
+  }
+  const float a = warp_sum((a0 + a1) + (a2 + a3));
+  if (lane == 0) hidden[static_cast<size_t>(b) * Cr + r] = fmaxf(a + b1[r], 0.f);
 }
 // gate[b][c] = sigmoid(W2[c] . hidden[b] + b2[c]): one warp per output channel, weight row in registers
 __global__ void __launch_bounds__(256)
@@ -446,7 +451,7 @@ int se_gelu_t(const void* x, void* out, int B, int HW, int C, int Cr, const floa
   se_mean_kernel<T><<<g1, 256, 0, s>>>(static_cast<const T*>(x), mean, HW, C);
   // no extra scratch: fc1 writes the hidden vectors [B, Cr] into the gate buffer, fc2 reads them from there and
   // writes the gates [B, C] over the (now consumed) means, which the scale kernel then reads
-  FVLA_REQUIRE(C <= 4096 && Cr <= 256 && Cr <= C, "se_gelu: channel counts out of range");
+  FVLA_REQUIRE(C % 4 == 0 && Cr <= 256 && Cr <= C, "se_gelu: channel counts out of range");
   float* hidden = gate;
   float* gates = mean;
   se_fc1_kernel<<<dim3(Cr, ceil_div(B, 8)), 256, 0, s>>>(mean, w1, b1, hidden, B, C, Cr);
