@@ -19,13 +19,14 @@
 //     -> planes      [32 ch][22 rows][TW+8 px]  bf16               one image plane per channel
 //   ldmatrix.x4 (A fragments, rows interleaved even/odd so kernel row ky+1 reuses half of ky's tiles)
 //     + Toeplitz B fragments from a 9-word-per-kernel-row table -> 7*NB mma.sync per (channel, 16 x 8NB px)
-//   fp32 accumulators (+bias) -> bf16 -> output planes -> LDS.32 + stmatrix.x4.trans
-//     -> staging     [16 rows][TW px][32 ch]  (swizzled)           natural NHWC order
-//   TMA store.
+//   fp32 accumulators (+bias) -> bf16 -> output planes (over the channel's own input plane)
+//     -> LDS.32 + stmatrix.x4.trans into a per-warp 8 px x 32 ch buffer -> 64-byte runs to global memory.
 //
-// CTA = 256 threads, tile = 16 rows x TW px x 32 channels, ~98 KB of shared memory -> 2 CTAs per SM so one
-// CTA's loads/stores overlap the other's math.  Algorithmic traffic: read + write the map once
-// (4 B per output element in bf16); the halo re-reads (22 x 40 / 16 x 32 = 1.7x) are served by L2.
+// CTA = 256 threads, tile = 16 rows x TW px x 32 channels, ~105 KB of shared memory -> 2 persistent CTAs per SM,
+// each prefetching its next tile's first slabs while it computes.  Algorithmic traffic: read + write the map once
+// (4 B per output element in bf16); the halo re-reads (22 x 40 / 16 x 32 = 1.7x) are served by L2 (ncu: DRAM
+// bytes = algorithmic).  The kernel is bound by shared-memory bandwidth (~520 KB through smem per 64 KB of HBM
+// traffic; budget in DESIGN.md 3.3), not by the tensor pipe (29 % busy) or HBM.
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx_sm100.cuh"
