@@ -14,6 +14,7 @@ FastVLM-0.5B + FastVLA head.  Prints ONE JSON line (see the task contract); rank
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -208,7 +209,8 @@ def main() -> None:
 
     cfg = FastVLAConfig(vlm_model_name=f"synthetic:{args.model}", state_dim=STATE_DIM, action_dim=ACTION_DIM,
                         compute_dtype="bfloat16", image_token_mode="prefix")
-    policy = FastVLAPolicy(cfg).to(dev).eval()
+    with contextlib.redirect_stdout(sys.stderr):  # the adapter logs its image size like the reference; stdout = the JSON line only
+        policy = FastVLAPolicy(cfg).to(dev).eval()
     engine = policy.model.backbone.model.engine  # builds + uploads weights
     images_h, states_h, tasks = make_batch(args.batch, seed=100 + rank)
     tasks_n = policy.processor.prepare_tasks(tasks, batch_size=args.batch)

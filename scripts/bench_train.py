@@ -14,6 +14,7 @@ prints one JSON line.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -51,7 +52,8 @@ def main() -> None:
 
     cfg = FastVLAConfig(vlm_model_name=f"synthetic:{args.model}", state_dim=STATE_DIM, action_dim=ACTION_DIM,
                         compute_dtype="bfloat16", image_token_mode="prefix")
-    policy = FastVLAPolicy(cfg).to(dev).train()
+    with contextlib.redirect_stdout(sys.stderr):
+        policy = FastVLAPolicy(cfg).to(dev).train()
     g = torch.Generator().manual_seed(11 + rank)
     batch = {"images": torch.rand(args.batch, 3, *IMG_HW, generator=g).to(dev),
              "states": torch.randn(args.batch, STATE_DIM, generator=g).to(dev),
