@@ -20,12 +20,17 @@ ap.add_argument("--model", default="fastvlm-0.5b")
 ap.add_argument("--batch", type=int, default=2)
 ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--hw", type=int, nargs=2, default=[480, 480])
+ap.add_argument("--bf16-weights", action="store_true",
+                help="round every weight matrix / conv kernel to bf16 first (a bf16-stored checkpoint): isolates "
+                     "arithmetic error from weight quantisation")
 a = ap.parse_args()
 arch = PRESETS[a.model]
 dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
 S_DIM = A_DIM = 14
 sd = synthetic_backbone_state_dict(arch, 0)
 hsd = synthetic_head_state_dict(arch.text.hidden, S_DIM, A_DIM, 1024, 1024, 1)
+if a.bf16_weights:
+    sd = {k: (v.bfloat16().float() if v.is_floating_point() and v.ndim >= 2 else v) for k, v in sd.items()}
 g = torch.Generator().manual_seed(1)
 B, T = a.batch, 17
 images = torch.rand(B, 3, a.hw[0], a.hw[1], generator=g)

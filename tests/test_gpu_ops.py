@@ -214,6 +214,35 @@ def test_dwconv7_tensor_core(native, B, H, W, C):
     assert torch.equal(patch, want), "impulse response != taps"
 
 
+@pytest.mark.parametrize("B,H,W,C", [(1, 8, 32, 32), (2, 16, 64, 96), (3, 40, 96, 64), (5, 128, 128, 192),
+                                     (8, 256, 256, 96), (2, 64, 64, 384), (2, 24, 48, 128), (1, 8, 16, 64)])
+def test_dwconv3_tma(native, B, H, W, C, monkeypatch):
+    """Persistent TMA-fed depthwise 3x3 (fp32 FFMA2 taps): single-tile and many-tiles-per-CTA grids (the 3-slot
+    ring wraps and its barrier parity flips), borders inside / between tiles and between images, per-channel
+    distinct taps.  The kernel accumulates in fp32, so each output is the fp32 conv rounded once to bf16."""
+    dev = _dev()
+    monkeypatch.setenv("FVLA_ENABLE_DWCONV3_TMA", "1")
+    g = torch.Generator().manual_seed(B * 977 + H + W + C)
+    x = torch.randn(B, C, H, W, generator=g).to(dev)
+    w = (torch.randn(C, 1, 3, 3, generator=g) / 3).to(dev)
+    b = torch.randn(C, generator=g).to(dev)
+    xin = x.permute(0, 2, 3, 1).contiguous().bfloat16()
+    out = native.op_dwconv(xin, _pack_dw(w), b, 3, 1, 1, 0).float()
+    ref = F.conv2d(xin.double().permute(0, 3, 1, 2), w.double(), b.double(), padding=1, groups=C).permute(0, 2, 3, 1)
+    err = (out.double() - ref).abs()
+    bound = ref.abs() * 2.0 ** -8 + 1e-5  # one bf16 rounding (half an ulp <= 2^-9 relative) + fp32 summation slack
+    assert bool((err <= bound).all()), f"dwconv3: worst excess {(err - bound).max().item():.3e}"
+    # an impulse reads the taps back (flipped), bf16-rounded once
+    imp = torch.zeros(1, H, W, C, device=dev, dtype=torch.bfloat16)
+    imp[0, H // 2, W // 2, :] = 1.0
+    o = native.op_dwconv(imp, _pack_dw(w), torch.zeros(C, device=dev), 3, 1, 1, 0).float()
+    patch = o[0, H // 2 - 1:H // 2 + 2, W // 2 - 1:W // 2 + 2, :]
+    want = w.bfloat16().float()[:, 0].flip(1, 2).permute(1, 2, 0)
+    assert torch.equal(patch, want), "impulse response != taps"
+    o[0, H // 2 - 1:H // 2 + 2, W // 2 - 1:W // 2 + 2, :] = 0
+    assert not bool(o.any()), "impulse leaked outside its 3x3 neighbourhood"
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_stem_conv(native, dtype):
     dev = _dev()

@@ -95,6 +95,11 @@ int dwconv7_mma_prepare(const float* w_packed, int C, uint32_t* wtab, cudaStream
 int dwconv7_mma(const void* in, const uint32_t* wtab, const float* bias, void* out, int B, int H, int W,
                 int C, cudaStream_t stream);
 
+// persistent TMA-fed depthwise 3x3 (bf16, stride 1, no activation, C%32==0, H%8==0, W%32==0), fp32 FFMA2 taps: dwconv3_tma.cu
+bool dwconv3_tma_supported(int dtype, int H, int W, int C, int mult, int k, int stride, int act);
+int dwconv3_tma(const void* in, const float* w_packed, const float* bias, void* out, int B, int H, int W, int C,
+                cudaStream_t stream);
+
 // smem-tiled bf16 fast path (stride 1, mult 1, k in {3,7}, W%64==0, H%8==0, C%32==0); dwconv() uses it
 bool dwconv_tiled_supported(int dtype, int H, int W, int C, int mult, int k, int stride);
 int dwconv_tiled(const void* in, const float* w_packed, const float* bias, void* out, int B, int H,
