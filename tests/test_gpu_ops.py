@@ -104,6 +104,28 @@ def test_gemm_bf16_inplace_residual(native):
     _close(out, ref, BF16_TOL, "gemm in-place residual")
 
 
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
+@pytest.mark.parametrize("M,N,K", [(272, 896, 896), (777, 448, 320), (17408, 896, 4864), (300, 40, 64)])
+def test_gemm_bf16_fp32_stream(native, M, N, K, bn):
+    """Decoder residual-stream epilogue: bf16 operands, FP32 residual in, FP32 out (in place), every tile width;
+    ragged M / N (N = 40: partial 32-column store boxes).  The fp32 result carries no output rounding, so the
+    tolerance is the accumulation-order slack only."""
+    if M > 4096 and bn not in (0, 256):
+        pytest.skip("large case only at the widths the engine picks")
+    dev = _dev()
+    g = torch.Generator().manual_seed(M + N + K + bn)
+    a = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    x = torch.randn(M, N, generator=g).to(dev)
+    ref = (a.double() @ w.double().t() + x.double()).float()
+    out = native.op_gemm(a, w, resid=x, out=x, block_n=bn)          # as the engine calls it: in place, no bias
+    assert out.data_ptr() == x.data_ptr() and out.dtype == torch.float32
+    _close(out, ref, 2e-5, f"gemm fp32 stream M={M} N={N} K={K} bn={bn}")
+    out2 = native.op_gemm(a, w, bias=bias, out_f32=True, block_n=bn)  # no residual, bias
+    _close(out2, (a.double() @ w.double().t() + bias.double()).float(), 2e-5, "gemm fp32 out + bias")
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("M,I,K", [(272, 4864, 896), (100, 256, 128), (1000, 640, 64)])
 def test_gemm_swiglu(native, dtype, M, I, K):
@@ -221,7 +243,7 @@ def test_dwconv3_tma(native, B, H, W, C, monkeypatch):
     ring wraps and its barrier parity flips), borders inside / between tiles and between images, per-channel
     distinct taps.  The kernel accumulates in fp32, so each output is the fp32 conv rounded once to bf16."""
     dev = _dev()
-    monkeypatch.setenv("FVLA_ENABLE_DWCONV3_TMA", "1")
+    monkeypatch.delenv("FVLA_DISABLE_DWCONV3_TMA", raising=False)
     g = torch.Generator().manual_seed(B * 977 + H + W + C)
     x = torch.randn(B, C, H, W, generator=g).to(dev)
     w = (torch.randn(C, 1, 3, 3, generator=g) / 3).to(dev)

@@ -650,7 +650,7 @@ int Engine::tap(int stage, const void* src, size_t bytes, size_t off, cudaStream
 // Forward
 // ---------------------------------------------------------------------------------------------
 int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, const void* resid,
-                     bool swiglu, cudaStream_t s, bool ab_f16) {
+                     bool swiglu, cudaStream_t s, bool ab_f16, bool out_f32) {
   GemmArgs g;
   g.A = A; g.lda = w.K;
   g.W = w.w; g.ldw = w.K;
@@ -661,6 +661,7 @@ int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, con
   g.act = (act == ACT_GELU && w.half_in) ? static_cast<int>(ACT_GELU_HALF) : act;
   g.swiglu = swiglu ? 1 : 0;
   g.ab_f16 = ab_f16 ? 1 : 0;
+  g.out_f32 = (out_f32 && cfg.dtype == FVLA_BF16) ? 1 : 0;  // the fp32 mode's D is FP32 anyway
   ++launches;
   const double fl = 2.0 * M * static_cast<double>(w.N) * w.K;
   flops += fl;
@@ -762,7 +763,7 @@ int Engine::reserve(int B, int n_tokens) {
   const size_t Tm = static_cast<size_t>(n_tokens) + nimg;  // upper bound of the merged length
   const size_t rows = static_cast<size_t>(B) * Tm;
   const int qkv_n = (cfg.n_q_heads + 2 * cfg.n_kv_heads) * cfg.head_dim;
-  if (int rc = ensure("dec_x", rows * H * e, &p)) return rc;
+  if (int rc = ensure("dec_x", rows * H * 4, &p)) return rc;  // residual stream: FP32 in either mode
   if (int rc = ensure("dec_xn", rows * H * e, &p)) return rc;
   if (int rc = ensure("dec_qkv", rows * qkv_n * e, &p)) return rc;
   if (int rc = ensure("dec_ao", rows * cfg.n_q_heads * cfg.head_dim * e, &p)) return rc;
@@ -1023,16 +1024,30 @@ int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image
   ++launches;
   prof_scope_ = "llm.";
   prof_begin(s);
-  if (int rc = embed_splice(cfg.dtype, embed_, img_tok, nimg, d_plan, X, B, Tm, H, s)) return rc;
-  prof_end("llm.embed_splice", 0.0, 2.0 * M * static_cast<double>(H) * e, s);
-  if (int rc = tap(FVLA_TAP_EMBEDS, X, static_cast<size_t>(M) * H * e, 0, s)) return rc;
+  // The residual stream X is FP32 in both precision modes: in bf16 mode every o-proj / down-proj epilogue adds
+  // its fp32 accumulator to the fp32 stream (no rounding of the stream per layer), RMSNorm reads it and writes the
+  // bf16 GEMM operand.  Taps of the stream are converted to the engine dtype.
+  const int stream32 = cfg.dtype == FVLA_BF16 ? 1 : 0;
+  auto tap_stream = [&](int stage) -> int {
+    auto it = taps_.find(stage);
+    if (it == taps_.end()) return 0;
+    const size_t need = static_cast<size_t>(M) * H * e;
+    if (static_cast<int64_t>(need) > it->second.second) {
+      set_error("tap buffer for stage " + std::to_string(stage) + " too small: need " + std::to_string(need) + " bytes");
+      return 2;
+    }
+    return convert(DT_F32, X, cfg.dtype, it->second.first, static_cast<long long>(M) * H, s);
+  };
+  if (int rc = embed_splice(cfg.dtype, embed_, img_tok, nimg, d_plan, X, B, Tm, H, s, stream32)) return rc;
+  prof_end("llm.embed_splice", 0.0, M * static_cast<double>(H) * (e + 4), s);
+  if (int rc = tap_stream(FVLA_TAP_EMBEDS)) return rc;
   const int nq = cfg.n_q_heads, nkv = cfg.n_kv_heads, hd = cfg.head_dim;
   for (int l = 0; l < cfg.n_layers; ++l) {
     DecLayer& L = layers_[l];
     ++launches;
     prof_begin(s);
-    if (int rc = rmsnorm(cfg.dtype, X, L.ln1, Xn, M, H, cfg.rms_eps, s)) return rc;
-    prof_end("llm.rmsnorm", 0.0, 2.0 * M * static_cast<double>(H) * e, s);
+    if (int rc = rmsnorm(cfg.dtype, X, L.ln1, Xn, M, H, cfg.rms_eps, s, stream32)) return rc;
+    prof_end("llm.rmsnorm", 0.0, M * static_cast<double>(H) * (e + 4), s);
     if (int rc = run_gemm(L.qkv, Xn, QKV, M, ACT_NONE, nullptr, false, s)) return rc;
     AttnArgs at;
     at.q = QKV; at.k = QKV + static_cast<size_t>(nq * hd) * e; at.v = QKV + static_cast<size_t>((nq + nkv) * hd) * e;
@@ -1050,22 +1065,22 @@ int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image
     if (int rc = attention(cfg.dtype, at, s)) return rc;
     prof_end("llm.attention T" + std::to_string(Tm), 2.0 * B * static_cast<double>(Tm) * Tm * nq * hd,
              static_cast<double>(M) * e * ((nq + 2 * nkv) * hd + nq * hd), s);
-    if (int rc = run_gemm(L.o, AO, X, M, ACT_NONE, X, false, s)) return rc;
+    if (int rc = run_gemm(L.o, AO, X, M, ACT_NONE, X, false, s, false, true)) return rc;
     ++launches;
     prof_begin(s);
-    if (int rc = rmsnorm(cfg.dtype, X, L.ln2, Xn, M, H, cfg.rms_eps, s)) return rc;
-    prof_end("llm.rmsnorm", 0.0, 2.0 * M * static_cast<double>(H) * e, s);
+    if (int rc = rmsnorm(cfg.dtype, X, L.ln2, Xn, M, H, cfg.rms_eps, s, stream32)) return rc;
+    prof_end("llm.rmsnorm", 0.0, M * static_cast<double>(H) * (e + 4), s);
     if (int rc = run_gemm(L.gate_up, Xn, ACTB, M, ACT_NONE, nullptr, true, s)) return rc;
-    if (int rc = run_gemm(L.down, ACTB, X, M, ACT_NONE, X, false, s)) return rc;
-    if (int rc = tap(FVLA_TAP_LAYER0 + l, X, static_cast<size_t>(M) * H * e, 0, s)) return rc;
+    if (int rc = run_gemm(L.down, ACTB, X, M, ACT_NONE, X, false, s, false, true)) return rc;
+    if (int rc = tap_stream(FVLA_TAP_LAYER0 + l)) return rc;
   }
   // ---- final norm + pooling ----
   float* pooled = static_cast<float*>(ws_.bufs["pooled"].first);
   ++launches;
   prof_begin(s);
-  if (int rc = pool_norm(cfg.dtype, X, final_norm_, d_pidx, d_lens, cfg.pool_mode, pooled, B, Tm, H,
+  if (int rc = pool_norm(DT_F32, X, final_norm_, d_pidx, d_lens, cfg.pool_mode, pooled, B, Tm, H,
                          cfg.rms_eps, s)) return rc;
-  prof_end("llm.pool_norm", 0.0, static_cast<double>(B) * H * (e + 4), s);
+  prof_end("llm.pool_norm", 0.0, static_cast<double>(B) * H * 8, s);
   if (int rc = tap(FVLA_TAP_POOLED, pooled, static_cast<size_t>(B) * H * 4, 0, s)) return rc;
   if (a.pooled != nullptr)
     FVLA_CUDA_CHECK(cudaMemcpyAsync(a.pooled, pooled, static_cast<size_t>(B) * H * 4,

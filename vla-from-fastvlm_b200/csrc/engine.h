@@ -95,7 +95,7 @@ class Engine {
   int tap(int stage, const void* src, size_t bytes, size_t dst_offset_bytes, cudaStream_t s);
 
   int run_gemm(const GemmW& w, const void* A, void* D, int M, int act, const void* resid, bool swiglu,
-               cudaStream_t s, bool ab_f16 = false);
+               cudaStream_t s, bool ab_f16 = false, bool out_f32 = false);
   int run_ffn(const VisBlock& blk, const void* z, void* hid, void* out_resid, int M, cudaStream_t s);
   int run_dw(const DwW& w, const void* in, void* out, int B, int H, int W, cudaStream_t s);
   int vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats, cudaStream_t s);

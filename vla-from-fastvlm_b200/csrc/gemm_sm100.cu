@@ -58,11 +58,12 @@ struct EpiParams {
   int ldr;
   int act;
   int ab_f16;                  // operands are fp16 (instruction descriptor formats), else bf16
+  int out_f32;                 // D and resid are FP32 (the decoder's residual stream): two 32-column TMA stores per sub-tile
 };
 
 using namespace epi;
 
-template <int BLOCK_N, bool SWIGLU>
+template <int BLOCK_N, bool SWIGLU, bool OUT_F32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_w,
@@ -216,7 +217,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // the TMA store this warp issued from its slab last time must have finished reading it
         if (lane == 0) ptx::tma_store_wait_read<0>();
         __syncwarp();
-        if (!SWIGLU && p.resid != nullptr) {
+        if (!SWIGLU && !OUT_F32 && p.resid != nullptr) {
           // residual sub-tile (32 rows x 128 B): coalesced 16-byte loads into the slab
           uint4 rr[8];
 #pragma unroll
@@ -251,6 +252,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int hp = 0; hp < ACC_PER_SUB / 32; ++hp) {
           uint32_t r[32];
           ptx::tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(acc_col0 + hp * 32), r);
+          if constexpr (OUT_F32) {
+            // FP32 output: the 4 KB slab holds 32 rows x 32 columns, so a sub-tile leaves in two halves
+            if (hp > 0) {
+              if (lane == 0) ptx::tma_store_wait_read<0>();
+              __syncwarp();
+            }
+          }
           // bias for these 32 columns: issued under the TMEM load so the two latencies overlap
           const int nb = n0 + acc_col0 + hp * 32;  // global column of v[0]
           const bool bias_vec = !SWIGLU && p.bias != nullptr && nb + 32 <= p.N;
@@ -323,6 +331,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
             }
+            if constexpr (OUT_F32) {
+              // The residual stream is updated IN PLACE (resid == D, checked on the host): the slab carries the
+              // fp32 accumulators and the TMA store adds them to D in L2 (cp.reduce.async.bulk .add) — no
+              // residual read in the epilogue at all.
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint32_t dst = sbase + ((c ^ (lane & 7)) << 4);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                             "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                             : "memory");
+              }
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (p.resid != nullptr) ptx::tma_reduce_add_2d(&tmap_d, out_col0 + hp * 32, m0 + ew * 32, slab);
+                else ptx::tma_store_2d(&tmap_d, out_col0 + hp * 32, m0 + ew * 32, slab);
+                ptx::tma_store_commit();
+              }
+              continue;
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const int chunk = hp * 4 + c;
@@ -348,11 +376,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
         }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::tma_store_2d(&tmap_d, out_col0, m0 + ew * 32, slab);
-          ptx::tma_store_commit();
+        if constexpr (!OUT_F32) {
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_d, out_col0, m0 + ew * 32, slab);
+            ptx::tma_store_commit();
+          }
         }
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
@@ -420,11 +450,30 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, long long 
 
 namespace {
 
-template <int BLOCK_N, bool SWIGLU>
+// FP32 output [rows, cols]: 32-row x 32-column (128-byte) store boxes through the same swizzled 4 KB slabs
+int make_tmap_f32_store(CUtensorMap* out, void* ptr, long long rows, long long cols, long long ld) {
+  TmaEncodeTiledFn fn = tma_encode_fn();
+  FVLA_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  FVLA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "TMA base must be 16-byte aligned");
+  FVLA_REQUIRE((ld * 4) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32 D) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 1;
+  }
+  return 0;
+}
+
+template <int BLOCK_N, bool SWIGLU, bool OUT_F32 = false>
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   static bool attr_set = false;
-  auto kfn = gemm_bf16_tcgen05_kernel<BLOCK_N, SWIGLU>;
+  auto kfn = gemm_bf16_tcgen05_kernel<BLOCK_N, SWIGLU, OUT_F32>;
   if (!attr_set) {
     FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES));
@@ -434,11 +483,15 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if (int rc = make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, BLOCK_M)) return rc;
   if (int rc = make_tmap_bf16(&tw, g.W, g.N, g.K, g.ldw, Cfg::HALF_N)) return rc;
   const int n_out = SWIGLU ? g.N / 2 : g.N;
-  if (int rc = make_tmap_bf16(&td, g.D, g.M, n_out, g.ldd, 32)) return rc;  // per-quarter 32-row stores
+  if (OUT_F32) {
+    if (int rc = make_tmap_f32_store(&td, g.D, g.M, n_out, g.ldd)) return rc;
+  } else if (int rc = make_tmap_bf16(&td, g.D, g.M, n_out, g.ldd, 32)) {  // per-quarter 32-row stores
+    return rc;
+  }
   EpiParams ep;
   ep.M = g.M; ep.N = g.N; ep.K = g.K;
   ep.bias = g.bias; ep.row_scale = g.row_scale;
-  ep.resid = static_cast<const __nv_bfloat16*>(g.resid); ep.ldr = g.ldr; ep.act = g.act; ep.ab_f16 = g.ab_f16;
+  ep.resid = static_cast<const __nv_bfloat16*>(g.resid); ep.ldr = g.ldr; ep.act = g.act; ep.ab_f16 = g.ab_f16; ep.out_f32 = g.out_f32;
   const int tiles = ceil_div(g.M, PAIR_M) * ceil_div(g.N, BLOCK_N);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
@@ -486,6 +539,9 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
                  "SwiGLU epilogue takes interleaved gate/up columns and no bias/residual/activation");
   }
   if (g.resid != nullptr) FVLA_REQUIRE(g.ldr % 8 == 0, "residual pitch must be a multiple of 8");
+  if (g.out_f32)
+    FVLA_REQUIRE(!g.swiglu && g.act != ACT_GELU_HALF_F16 && (g.resid == nullptr || (g.resid == g.D && g.ldr == g.ldd)),
+                 "fp32 output: plain / bias / activation epilogues; a residual must be D itself (in-place stream update)");
   if (g.act == ACT_GELU_HALF_F16)
     FVLA_REQUIRE(g.resid == nullptr && !g.swiglu, "the fp16-output GELU epilogue takes no residual");
   const int bn = g.block_n > 0 ? g.block_n : pick_block_n(g.M, g.N, g.swiglu != 0);
@@ -493,6 +549,14 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     switch (bn) {
       case 256: return launch_gemm<256, true>(g, stream);
       case 128: return launch_gemm<128, true>(g, stream);
+      default: break;
+    }
+  } else if (g.out_f32) {
+    switch (bn) {
+      case 256: return launch_gemm<256, false, true>(g, stream);
+      case 192: return launch_gemm<192, false, true>(g, stream);
+      case 128: return launch_gemm<128, false, true>(g, stream);
+      case 64: return launch_gemm<64, false, true>(g, stream);
       default: break;
     }
   } else {

@@ -24,6 +24,8 @@ struct GemmArgs {
   int swiglu = 0;                         // columns are interleaved (gate, up): out = silu(g) * u
   int block_n = 0;                        // 0 = auto (bf16 path only)
   int ab_f16 = 0;                         // bf16 path: A and W hold FP16 bits (fp16 x fp16 -> fp32 MMA)
+  int out_f32 = 0;                        // bf16 path: D is FP32 (ldd in fp32 elements); resid must be null or D itself
+                                          // (in-place stream update, done as a TMA reduce-add)
 };
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);  // tcgen05 + TMA + TMEM
 int gemm_f32(const GemmArgs& g, cudaStream_t stream);   // FFMA, fp32 parity mode
@@ -130,11 +132,13 @@ bool attention_v2_supported(const AttnArgs& a);
 int attention_v2(const AttnArgs& a, cudaStream_t stream);  // reference-grade SIMT for either dtype
 
 // ---- Qwen2 glue ------------------------------------------------------------------------------
+// x_f32 (bf16 mode only): x is the decoder's FP32 residual stream, out stays bf16
 int rmsnorm(int dtype, const void* x, const float* weight, void* out, int rows, int H, float eps,
-            cudaStream_t stream);
+            cudaStream_t stream, int x_f32 = 0);
 // plan[b*T+t]: >=0 vocab id, -1 zero row (padding), <=-2 image row (-2-idx) of sample b
+// out_f32 (bf16 mode only): write the rows as FP32 (the decoder's residual stream)
 int embed_splice(int dtype, const void* table, const void* img_feats, int n_img, const int* plan,
-                 void* out, int B, int T, int H, cudaStream_t stream);
+                 void* out, int B, int T, int H, cudaStream_t stream, int out_f32 = 0);
 // mode 0: last_token at pool_idx[b]; mode 1: mean over t < len[b]. Applies the final RMSNorm.
 int pool_norm(int dtype, const void* hidden, const float* norm_w, const int* pool_idx,
               const int* lens, int mode, float* pooled, int B, int T, int H, float eps,

@@ -8,42 +8,43 @@ namespace {
 
 // Qwen2RMSNorm (transformers/models/qwen2/modeling_qwen2.py: Qwen2RMSNorm.forward):
 //   y = weight * (x * rsqrt(mean(x^2) + eps)), statistics in fp32.
-template <typename T>
+template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
-rmsnorm_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ out, int H,
+rmsnorm_kernel(const TI* __restrict__ x, const float* __restrict__ w, TO* __restrict__ out, int H,
                float eps) {
   __shared__ float red[32];
   const size_t row = blockIdx.x;
-  const T* xr = x + row * H;
+  const TI* xr = x + row * H;
   float ss = 0.f;
   for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
-    Vec8<T> v; v.load(xr + i);
+    Vec8<TI> v; v.load(xr + i);
 #pragma unroll
     for (int c = 0; c < 8; ++c) ss = fmaf(v.v[c], v.v[c], ss);
   }
   ss = block_sum(ss, red);
   const float rstd = rsqrtf(ss / static_cast<float>(H) + eps);
-  T* orow = out + row * H;
+  TO* orow = out + row * H;
   for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
-    Vec8<T> v; v.load(xr + i);
+    Vec8<TI> v; v.load(xr + i);
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + i));
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + i) + 1);
     const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    Vec8<TO> o;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) v.v[c] = v.v[c] * rstd * wv[c];
-    v.store(orow + i);
+    for (int c = 0; c < 8; ++c) o.v[c] = v.v[c] * rstd * wv[c];
+    o.store(orow + i);
   }
 }
 
 // LLaVA prepare_inputs_labels_for_multimodal, materialised from a per-position plan.
-template <typename T>
+template <typename T, typename TO>
 __global__ void embed_splice_kernel(const T* __restrict__ table, const T* __restrict__ img,
-                                    int n_img, const int* __restrict__ plan, T* __restrict__ out,
+                                    int n_img, const int* __restrict__ plan, TO* __restrict__ out,
                                     int T_len, int H) {
   const size_t pos = blockIdx.x;  // b*T + t
   const int b = static_cast<int>(pos / T_len);
   const int code = plan[pos];
-  T* dst = out + pos * H;
+  TO* dst = out + pos * H;
   const T* src = nullptr;
   if (code >= 0) src = table + static_cast<size_t>(code) * H;
   else if (code <= -2) src = img + (static_cast<size_t>(b) * n_img + (-2 - code)) * H;
@@ -54,7 +55,10 @@ __global__ void embed_splice_kernel(const T* __restrict__ table, const T* __rest
 #pragma unroll
       for (int c = 0; c < 8; ++c) v.v[c] = 0.f;
     }
-    v.store(dst + i);
+    Vec8<TO> o;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o.v[c] = v.v[c];
+    o.store(dst + i);
   }
 }
 
@@ -165,27 +169,34 @@ __global__ void rope_table_kernel(float* cos_t, float* sin_t, int T_len, int hal
 }  // namespace
 
 int rmsnorm(int dtype, const void* x, const float* weight, void* out, int rows, int H, float eps,
-            cudaStream_t stream) {
+            cudaStream_t stream, int x_f32) {
   FVLA_REQUIRE(H % 8 == 0 && rows > 0, "rmsnorm: H%8");
   if (dtype == DT_F32)
-    rmsnorm_kernel<float><<<rows, 128, 0, stream>>>(static_cast<const float*>(x), weight,
-                                                    static_cast<float*>(out), H, eps);
+    rmsnorm_kernel<float, float><<<rows, 128, 0, stream>>>(static_cast<const float*>(x), weight,
+                                                           static_cast<float*>(out), H, eps);
+  else if (x_f32)  // fp32 residual stream in, bf16 GEMM operand out
+    rmsnorm_kernel<float, __nv_bfloat16><<<rows, 128, 0, stream>>>(static_cast<const float*>(x), weight,
+                                                                   static_cast<__nv_bfloat16*>(out), H, eps);
   else
-    rmsnorm_kernel<__nv_bfloat16><<<rows, 128, 0, stream>>>(
+    rmsnorm_kernel<__nv_bfloat16, __nv_bfloat16><<<rows, 128, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(x), weight, static_cast<__nv_bfloat16*>(out), H, eps);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int embed_splice(int dtype, const void* table, const void* img_feats, int n_img, const int* plan,
-                 void* out, int B, int T, int H, cudaStream_t stream) {
+                 void* out, int B, int T, int H, cudaStream_t stream, int out_f32) {
   FVLA_REQUIRE(H % 8 == 0 && B > 0 && T > 0, "embed_splice: H%8");
   if (dtype == DT_F32)
-    embed_splice_kernel<float><<<B * T, 128, 0, stream>>>(
+    embed_splice_kernel<float, float><<<B * T, 128, 0, stream>>>(
         static_cast<const float*>(table), static_cast<const float*>(img_feats), n_img, plan,
         static_cast<float*>(out), T, H);
+  else if (out_f32)
+    embed_splice_kernel<__nv_bfloat16, float><<<B * T, 128, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(img_feats),
+        n_img, plan, static_cast<float*>(out), T, H);
   else
-    embed_splice_kernel<__nv_bfloat16><<<B * T, 128, 0, stream>>>(
+    embed_splice_kernel<__nv_bfloat16, __nv_bfloat16><<<B * T, 128, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(img_feats),
         n_img, plan, static_cast<__nv_bfloat16*>(out), T, H);
   FVLA_CUDA_CHECK(cudaGetLastError());

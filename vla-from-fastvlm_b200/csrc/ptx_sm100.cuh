@@ -71,6 +71,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, int x, int y,
                "r"(x), "r"(y), "r"(smem_src)
                : "memory");
 }
+// D[box] += smem (element-wise add performed in L2; the tensor map's data type selects the arithmetic)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, int x, int y, uint32_t smem_src) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(x), "r"(y), "r"(smem_src)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

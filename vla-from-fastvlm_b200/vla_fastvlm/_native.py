@@ -212,9 +212,10 @@ def stream_ptr() -> int:
 def op_gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
             resid: Optional[torch.Tensor] = None, act: int = ACT_NONE, swiglu: bool = False,
             row_scale: Optional[torch.Tensor] = None, block_n: int = 0,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
     """D = act(row_scale * A @ W^T + bias) + resid, A [M,K], W [N,K].
 
+    bf16 operands with an fp32 `out` (or out_f32=True) and fp32 `resid`: the decoder's residual-stream epilogue.
     fp16 operands (A and W both torch.float16) select the tensor-core path with fp16 x fp16 MMAs; the output is
     bf16 unless act == ACT_GELU_HALF_F16 (5), whose result is fp16 (the ConvFFN hidden tensor)."""
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1] and a.dtype == w.dtype
@@ -226,10 +227,16 @@ def op_gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     code = dtype_code(torch.bfloat16) if ab_f16 else dtype_code(a.dtype)
     if out is None:
         odt = torch.float16 if act == ACT_GELU_HALF_F16 else (torch.bfloat16 if ab_f16 else a.dtype)
+        if out_f32:
+            odt = torch.float32
         out = torch.empty((M, n_out), device=a.device, dtype=odt)
+    f32_stream = a.dtype != torch.float32 and out.dtype == torch.float32  # bf16 operands, fp32 D / resid
+    if f32_stream:
+        assert resid is None or resid.dtype == torch.float32
     check(load().fvla_op_gemm(code, ptr(a), K, ptr(w), K, ptr(out), out.stride(0), M, N,
                               K, ptr(bias), ptr(row_scale), ptr(resid),
-                              resid.stride(0) if resid is not None else 0, act, int(swiglu) | (2 if ab_f16 else 0),
+                              resid.stride(0) if resid is not None else 0, act,
+                              int(swiglu) | (2 if ab_f16 else 0) | (4 if f32_stream else 0),
                               block_n, stream_ptr()), "fvla_op_gemm")
     return out
 
