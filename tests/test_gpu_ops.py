@@ -379,11 +379,12 @@ def test_attention(native, B, N, hq, hkv, hd, causal, rope, impl, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_rmsnorm(native, dtype):
+@pytest.mark.parametrize("H", [896, 1536, 3584, 5120, 64])  # 5120: beyond the register-resident part of a row
+def test_rmsnorm(native, dtype, H):
     dev = _dev()
-    g = torch.Generator().manual_seed(9)
-    x = (torch.randn(333, 896, generator=g) * 3).to(dev).to(dtype)
-    w = torch.randn(896, generator=g).to(dev)
+    g = torch.Generator().manual_seed(9 + H)
+    x = (torch.randn(333, H, generator=g) * 3).to(dev).to(dtype)
+    w = torch.randn(H, generator=g).to(dev)
     out = native.op_rmsnorm(x, w, 1e-6)
     xf = x.float()
     ref = w * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6))
