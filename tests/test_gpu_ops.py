@@ -358,6 +358,9 @@ ATTN_CASES = [
     (1, 300, 12, 2, 128, True, False),     # head_dim 128, v2 kernel
     (2, 130, 4, 4, 64, False, False),      # v2 kernel, non-causal with a 2-key tail tile
     (1, 600, 4, 2, 64, True, False),       # v2 kernel, causal (N >= 512)
+    (3, 33, 28, 4, 128, True, False),      # grouped-query kernel: Qwen2-7B grouping (7 heads per kv head), ragged N
+    (2, 290, 8, 1, 64, True, False),       # grouped-query kernel: largest group (8 warps), 5 kv tiles
+    (2, 64, 6, 3, 64, True, False),        # grouped-query kernel: group of 2, N a multiple of the tile
 ]
 
 

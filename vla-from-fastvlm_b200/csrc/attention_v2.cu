@@ -8,6 +8,8 @@
 //   * the softmax scale is folded into one FFMA feeding ex2: p = 2^(s*c - m*c)
 //   * masking code only runs on tiles that need it (sequence tail, causal diagonal); warps whose rows
 //     lie entirely before a causal tile skip it
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -234,6 +236,193 @@ flash_attn_v2_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   }
 }
 
+// Grouped-query variant for the short causal Qwen2 prefill: a CTA owns 16 queries of ONE kv head and runs one warp
+// per query head of that group (7 for Qwen2-0.5B/7B, 6 for 1.5B), so a K/V tile is staged once for the whole group
+// instead of once per query head (registers cap an SM at ~16 warps either way).  Same fragment code as above with
+// every warp on the same 16 rows and its own head.
+template <int HD>
+__global__ void __launch_bounds__(256, (HD <= 64 ? 2 : 1))
+flash_attn_gqa_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                      const __nv_bfloat16* __restrict__ v, int ld, __nv_bfloat16* __restrict__ o, int ld_o,
+                      int N, int group, float scale_log2e) {
+  constexpr int LDS = HD + 8;
+  constexpr int LDSB = LDS * 2;
+  constexpr int KV_TILE_B = BKV2 * LDSB;
+  constexpr int VPR = HD / 8;
+  extern __shared__ __align__(16) uint8_t smem_a3[];
+  const uint32_t sK = static_cast<uint32_t>(__cvta_generic_to_shared(smem_a3));  // 2 stages
+  const uint32_t sV = sK + 2 * KV_TILE_B;                                         // 2 stages
+  const uint32_t sQ = sV + 2 * KV_TILE_B;                                         // [group][16 rows]
+
+  const int qb = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int nthr = blockDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const int h = hk * group + warp;  // this warp's query head
+  const size_t row0 = static_cast<size_t>(b) * N;
+  const __nv_bfloat16* kp = k + row0 * ld + hk * HD;
+  const __nv_bfloat16* vp = v + row0 * ld + hk * HD;
+  const int q0 = qb * 16;
+  const int kv_blocks = min((N + BKV2 - 1) / BKV2, (q0 + 16 + BKV2 - 1) / BKV2);
+
+  auto stage_kv = [&](int st, int tok0) {
+    for (int i = threadIdx.x; i < BKV2 * VPR; i += nthr) {
+      const int r = i / VPR, c = i % VPR;
+      const bool ok = tok0 + r < N;
+      const size_t off = ok ? static_cast<size_t>(tok0 + r) * ld + c * 8 : 0;
+      cpa16(sK + st * KV_TILE_B + r * LDSB + c * 16, kp + off, ok ? 16 : 0);
+      cpa16(sV + st * KV_TILE_B + r * LDSB + c * 16, vp + off, ok ? 16 : 0);
+    }
+  };
+  {  // Q: 16 rows of each head of the group (adjacent heads are adjacent columns of the qkv row)
+    const __nv_bfloat16* qg = q + row0 * ld + hk * group * HD;
+    for (int i = threadIdx.x; i < group * 16 * VPR; i += nthr) {
+      const int c = i % VPR, r = (i / VPR) % 16, w = i / (VPR * 16);
+      const bool ok = q0 + r < N;
+      const __nv_bfloat16* p = ok ? qg + static_cast<size_t>(q0 + r) * ld + w * HD + c * 8 : qg;
+      cpa16(sQ + (w * 16 + r) * LDSB + c * 16, p, ok ? 16 : 0);
+    }
+  }
+  stage_kv(0, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  uint32_t qf[HD / 16][4];
+  {
+    const uint32_t base = sQ + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDSB + (lane >> 4) * 16;
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) ldsm_x4(qf[ks], base + ks * 32);
+  }
+  float oacc[HD / 8][4];
+#pragma unroll
+  for (int j = 0; j < HD / 8; ++j) { oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  const int qrow = q0 + g;  // this thread's rows: qrow and qrow + 8
+
+  for (int kb = 0; kb < kv_blocks; ++kb) {
+    const int st = kb & 1;
+    if (kb + 1 < kv_blocks) stage_kv(st ^ 1, (kb + 1) * BKV2);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int key0 = kb * BKV2;
+    const uint32_t kt = sK + st * KV_TILE_B, vt = sV + st * KV_TILE_B;
+    float s[BKV2 / 8][4];
+#pragma unroll
+    for (int j = 0; j < BKV2 / 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < BKV2 / 8; j += 2) {
+      const uint32_t kaddr = kt + ((j + (lane >> 4)) * 8 + (lane & 7)) * LDSB + ((lane >> 3) & 1) * 16;
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        uint32_t kf[4];
+        ldsm_x4(kf, kaddr + ks * 32);
+        mma16816(s[j], qf[ks], kf[0], kf[1]);
+        mma16816(s[j + 1], qf[ks], kf[2], kf[3]);
+      }
+    }
+    if (key0 + BKV2 > N || key0 + BKV2 - 1 > q0) {  // sequence tail or causal diagonal
+#pragma unroll
+      for (int j = 0; j < BKV2 / 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = key0 + j * 8 + 2 * tig + (e & 1);
+          const int qi = qrow + (e >> 1) * 8;
+          if (key >= N || key > qi) s[j][e] = -INFINITY;
+        }
+      }
+    }
+    float mx[2] = {m_run[0], m_run[1]};
+#pragma unroll
+    for (int j = 0; j < BKV2 / 8; ++j) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float ms[2], corr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float msafe = mx[r] == -INFINITY ? 0.f : mx[r];
+      ms[r] = msafe * scale_log2e;
+      corr[r] = ex2f(m_run[r] * scale_log2e - ms[r]);
+      m_run[r] = mx[r];
+    }
+    float lsum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < BKV2 / 8; ++j) {
+      s[j][0] = ex2f(fmaf(s[j][0], scale_log2e, -ms[0]));
+      s[j][1] = ex2f(fmaf(s[j][1], scale_log2e, -ms[0]));
+      s[j][2] = ex2f(fmaf(s[j][2], scale_log2e, -ms[1]));
+      s[j][3] = ex2f(fmaf(s[j][3], scale_log2e, -ms[1]));
+      lsum[0] += s[j][0] + s[j][1];
+      lsum[1] += s[j][2] + s[j][3];
+    }
+    l_run[0] = fmaf(l_run[0], corr[0], lsum[0]);
+    l_run[1] = fmaf(l_run[1], corr[1], lsum[1]);
+#pragma unroll
+    for (int j = 0; j < HD / 8; ++j) {
+      oacc[j][0] *= corr[0]; oacc[j][1] *= corr[0];
+      oacc[j][2] *= corr[1]; oacc[j][3] *= corr[1];
+    }
+#pragma unroll
+    for (int kk = 0; kk < BKV2 / 16; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pk2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pk2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pk2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pk2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      const uint32_t vaddr = vt + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDSB + (lane >> 4) * 16;
+#pragma unroll
+      for (int jn = 0; jn < HD / 8; jn += 2) {
+        uint32_t vb[4];
+        ldsm_x4_t(vb, vaddr + jn * 16);
+        mma16816(oacc[jn], pa, vb[0], vb[1]);
+        mma16816(oacc[jn + 1], pa, vb[2], vb[3]);
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
+  const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+  __nv_bfloat16* op = o + row0 * ld_o + h * HD;
+#pragma unroll
+  for (int j = 0; j < HD / 8; ++j) {
+    const int col = j * 8 + 2 * tig;
+    if (qrow < N)
+      *reinterpret_cast<uint32_t*>(op + static_cast<size_t>(qrow) * ld_o + col) = pk2(oacc[j][0] * inv0, oacc[j][1] * inv0);
+    if (qrow + 8 < N)
+      *reinterpret_cast<uint32_t*>(op + static_cast<size_t>(qrow + 8) * ld_o + col) = pk2(oacc[j][2] * inv1, oacc[j][3] * inv1);
+  }
+}
+
+template <int HD>
+int launch_gqa(const AttnArgs& a, cudaStream_t stream) {
+  auto kfn = flash_attn_gqa_kernel<HD>;
+  const int group = a.heads_q / a.heads_kv;
+  const int smem = (4 * BKV2 + 8 * 16) * (HD + 8) * 2;  // Q sized for the largest group
+  static bool attr_set = false;
+  if (!attr_set) {
+    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(a.N, 16), a.heads_kv, a.B);
+  kfn<<<grid, 32 * group, smem, stream>>>(static_cast<const __nv_bfloat16*>(a.q), static_cast<const __nv_bfloat16*>(a.k),
+                                          static_cast<const __nv_bfloat16*>(a.v), a.ld_qkv, static_cast<__nv_bfloat16*>(a.o),
+                                          a.ld_o, a.N, group, a.scale * 1.4426950408889634f);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 template <int HD, bool CAUSAL, int NWARPS>
 int launch_v2(const AttnArgs& a, cudaStream_t stream) {
   auto kfn = flash_attn_v2_kernel<HD, CAUSAL, NWARPS>;
@@ -260,7 +449,12 @@ bool attention_v2_supported(const AttnArgs& a) {
 }
 
 int attention_v2(const AttnArgs& a, cudaStream_t stream) {
-  const bool small = a.causal && a.N < 512;  // the short causal prefill: 64-query CTAs
+  const bool small = a.causal && a.N < 512;  // the short causal prefill
+  // grouped-query CTAs (one warp per query head of a kv group) when the group is 2..8 heads
+  static const bool gqa_on = std::getenv("FVLA_DISABLE_GQA_ATTN") == nullptr;  // A/B switch
+  if (gqa_on && small && a.heads_kv > 0 && a.heads_q % a.heads_kv == 0 && a.heads_q / a.heads_kv >= 2 &&
+      a.heads_q / a.heads_kv <= 8 && (a.head_dim == 64 || a.head_dim == 128))
+    return a.head_dim == 64 ? launch_gqa<64>(a, stream) : launch_gqa<128>(a, stream);
   if (a.head_dim == 32) {
     if (small) return a.causal ? launch_v2<32, true, 4>(a, stream) : launch_v2<32, false, 4>(a, stream);
     return a.causal ? launch_v2<32, true, 8>(a, stream) : launch_v2<32, false, 8>(a, stream);
