@@ -94,7 +94,37 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
 
+    # NVML throttle-reason bits (nvml.h: nvmlClocksEventReason*)
+    _BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def _run_nvml(self) -> bool:
+        """Sample through NVML every 20 ms (a 10-step timed region lasts < 1 s; nvidia-smi manages 2-3 samples)."""
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            reasons_fn(h)
+        except Exception:
+            return False
+        while not self._stop.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                mask = int(reasons_fn(h))
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append([str(sm), str(mx), f"{pw:.1f}"] +
+                                    ["Active" if mask & bit else "Not Active" for _, bit in self._BITS])
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+        return True
+
     def _run(self) -> None:
+        if self._run_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
