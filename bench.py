@@ -199,7 +199,7 @@ def main() -> None:
     ap.add_argument("--model", default="fastvlm-0.5b")
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-samples", type=int, default=2)
+    ap.add_argument("--cpu-samples", type=int, default=16, help="oracle forwards timed for cpu_baseline (~0.7 s each)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
