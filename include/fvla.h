@@ -118,6 +118,15 @@ int64_t fvla_weight_bytes(fvla_engine* e);
 /* The hot path: FastVLMWithExpert.forward (fastvlm_with_expert.py:40-54). */
 int fvla_forward(fvla_engine* e, const fvla_forward_args* args, void* stream);
 
+/* LeRobot's NormalizerProcessorStep (STATE, mean/std) and UnnormalizerProcessorStep (ACTION) run as separate
+ * elementwise passes around the policy (lerobot_fastvla/processor_fastvla.py:30-48).  Here they are the first and last
+ * arithmetic of the action-head kernel:  state' = (state - state_mean) * state_inv_std;
+ * action' = action * action_scale + action_shift.  HOST fp32 vectors ([state_dim], [state_dim], [action_dim],
+ * [action_dim]); any may be NULL (identity for that part).  Takes effect from the next fvla_forward; call after
+ * fvla_finalize.  With all four NULL the head computes exactly FastVLMWithExpert.forward. */
+int fvla_set_io_normalization(fvla_engine* e, const float* state_mean, const float* state_inv_std,
+                              const float* action_scale, const float* action_shift);
+
 /* Number of kernels the last fvla_forward launched, and algorithmic FLOPs (SURVEY §8d formula). */
 int64_t fvla_last_launch_count(fvla_engine* e);
 double fvla_last_forward_flops(fvla_engine* e);
@@ -179,6 +188,10 @@ int fvla_op_attention(int32_t dtype, int32_t impl, const void* q, const void* k,
                       int32_t causal, const float* rope_cos, const float* rope_sin, void* stream);
 int fvla_op_rmsnorm(int32_t dtype, const void* x, const float* weight, void* out, int32_t rows,
                     int32_t H, float eps, void* stream);
+/* FastViTHD `LayerNormChannel` [EXT mci.py] without its affine part (folded into the qkv GEMM by fvla_finalize):
+ * per row of x [rows, C]: out = (x - mean) * rsqrt(var + eps), statistics in fp32 */
+int fvla_op_layernorm_rows(int32_t dtype, const void* x, void* out, int32_t rows, int32_t C, float eps,
+                           void* stream);
 /* FastViTHD ConvFFN tail fused on chip (bf16, C in {96,192}, hidden %128 == 0) [EXT convffn.fc1 -> GELU -> fc2,
  * + layer-scaled residual]: out = resid + w2 . gelu(w1 . x + b1) + b2.  w1 [hidden,C] and b1 are passed
  * PRE-HALVED (the epilogue evaluates gelu from x/2); w2 [C,hidden]; resid may alias out. */

@@ -91,6 +91,21 @@ def _bn(sd: Dict[str, Tensor], p: str, x: Tensor) -> Tensor:
                         sd[p + ".bias"], training=False, eps=1e-5)
 
 
+def _ln_channel(sd: Dict[str, Tensor], p: str, x: Tensor) -> Tensor:
+    """mci.py LayerNormChannel [EXT]: per-pixel statistics over the channel dimension of (B,C,H,W), biased variance,
+    eps 1e-5, per-channel weight and bias."""
+    u = x.mean(1, keepdim=True)
+    s = (x - u).pow(2).mean(1, keepdim=True)
+    x = (x - u) / torch.sqrt(s + 1e-5)
+    return sd[p + ".weight"].view(1, -1, 1, 1) * x + sd[p + ".bias"].view(1, -1, 1, 1)
+
+
+def _attn_norm(sd: Dict[str, Tensor], p: str, x: Tensor) -> Tensor:
+    """AttentionBlock.norm: the checkpoint's key set says which layer it is — BatchNorm2d carries running statistics,
+    LayerNormChannel does not (SURVEY App. A marks the choice unverified; both are restated)."""
+    return _bn(sd, p, x) if p + ".running_mean" in sd else _ln_channel(sd, p, x)
+
+
 def _conv_ffn(sd: Dict[str, Tensor], p: str, x: Tensor) -> Tensor:
     """mci.py ConvFFN.forward: dw7x7(no bias) -> BN -> fc1 -> GELU -> fc2."""
     d = x.shape[1]
@@ -140,7 +155,7 @@ def fastvithd_forward(sd: Dict[str, Tensor], x: Tensor, layers: Sequence[int], d
             p = P + f"network.{idx}.{j}"
             if attention[i]:
                 # AttentionBlock: x + ls1*MHSA(BN(x)); x + ls2*ConvFFN(x)
-                x = x + sd[p + ".layer_scale_1"] * _mhsa(sd, p + ".token_mixer", _bn(sd, p + ".norm", x), head_dim)
+                x = x + sd[p + ".layer_scale_1"] * _mhsa(sd, p + ".token_mixer", _attn_norm(sd, p + ".norm", x), head_dim)
                 x = x + sd[p + ".layer_scale_2"] * _conv_ffn(sd, p + ".convffn", x)
             else:
                 # RepMixerBlock: x = reparam dw3x3(x); x + ls*ConvFFN(x)
@@ -332,11 +347,15 @@ class FastVLAOracle:
 
     @torch.no_grad()
     def vlm_hidden(self, pixel: Tensor, input_ids: Tensor, attention_mask: Tensor,
-                   taps: Optional[Taps] = None) -> Tuple[Tensor, Tensor]:
+                   taps: Optional[Taps] = None, inject: Optional[Taps] = None) -> Tuple[Tensor, Tensor]:
         """LlavaQwen2ForCausalLM.forward(input_ids, attention_mask, images=pixel) minus the LM head:
-        returns hidden_states[-1] (B,T',H) and the merged mask."""
+        returns hidden_states[-1] (B,T',H) and the merged mask.  `inject["image_features"]` (test hook) replaces
+        the tower's output so that the segments after an ill-conditioned tower input can be checked on their own."""
         v, t = self.arch.vision, self.arch.text
-        feats = fastvithd_forward(self.sd, pixel, v.layers, v.dims, v.attention, v.pos_emb, v.head_dim, taps)
+        if inject is not None and "image_features" in inject:
+            feats = inject["image_features"].to(torch.float32).cpu()
+        else:
+            feats = fastvithd_forward(self.sd, pixel, v.layers, v.dims, v.attention, v.pos_emb, v.head_dim, taps)
         img_tok = mm_projector(self.sd, feats)
         if taps is not None:
             taps["projector"] = img_tok
@@ -350,11 +369,12 @@ class FastVLAOracle:
 
     @torch.no_grad()
     def forward(self, images: Tensor, states: Optional[Tensor], input_ids: Tensor, attention_mask: Tensor,
-                pool_idx: Optional[Tensor] = None, taps: Optional[Taps] = None) -> Tensor:
+                pool_idx: Optional[Tensor] = None, taps: Optional[Taps] = None,
+                inject: Optional[Taps] = None) -> Tensor:
         pixel = prepare_images(images, self.arch.vision.image_size, self.resize_with_padding, self.pad_value)
         if taps is not None:
             taps["preprocess"] = pixel
-        hidden, _ = self.vlm_hidden(pixel, input_ids, attention_mask, taps)
+        hidden, _ = self.vlm_hidden(pixel, input_ids, attention_mask, taps, inject)
         if pool_idx is not None:
             b, _, h = hidden.shape
             pooled = hidden.gather(1, pool_idx.view(b, 1, 1).expand(b, 1, h).long()).squeeze(1)

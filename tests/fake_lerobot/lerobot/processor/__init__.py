@@ -67,7 +67,7 @@ class UnnormalizerProcessorStep(_Step):
             mode = self.norm_map.get(ft.type.value)
             if k in self.stats and mode is not None and mode.value == "MEAN_STD":
                 s = self.stats[k]
-                return x * (s["std"].to(x.device) + 1e-8) + s["mean"].to(x.device)
+                return x * s["std"].to(x.device) + s["mean"].to(x.device)  # LeRobot: eps only on the forward side
         return x
 
 

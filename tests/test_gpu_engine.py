@@ -114,6 +114,69 @@ def test_engine_explicit_pool_idx_and_chunking(dtype):
     _run(dtype, "prefix", B=5, vision_chunk=2, explicit_pool=True)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_engine_layernorm_attention_norm(dtype):
+    """AttentionBlock.norm as LayerNormChannel (per-token statistics; a checkpoint without `norm.running_mean`): the
+    engine normalises at run time and folds only the affine part into qkv; the oracle restates the layer literally."""
+    _need_gpu()
+    from oracle.fastvla_oracle import FastVLAOracle
+    from vla_fastvlm import _native as N
+    from vla_fastvlm.model.synthetic import synthetic_backbone_state_dict
+
+    arch, _, hsd = tiny_weights(0)
+    sd = synthetic_backbone_state_dict(arch, 0, attn_norm="layernorm")
+    assert not any(k.endswith("norm.running_mean") and ".convffn." not in k for k in sd)
+    images, states, ids, mask = make_inputs(3, 120, 160, 9, arch.text.vocab, TINY_HEAD["state_dim"], seed=3)
+    taps = {}
+    ref = FastVLAOracle(arch, sd, hsd).forward(images, states, ids, mask, taps=taps)
+    ref_bn = FastVLAOracle(arch, tiny_weights(0)[1], hsd).forward(images, states, ids, mask)
+    assert (ref - ref_bn).abs().max() > 1e-3            # the two norms are different functions on these weights
+    eng = make_engine(arch, sd, hsd, dtype)
+    dev, v = eng.device, arch.vision
+    side = v.image_size // 4 // 8
+    stage3 = torch.zeros(3, side, side, v.dims[3], device=dev, dtype=dtype)
+    feats = torch.zeros(3, v.num_tokens, v.out_channels, device=dev, dtype=dtype)
+    eng.set_tap(N.TAP_VIS_STAGE0 + 3, stage3)
+    eng.set_tap(N.TAP_IMAGE_FEATURES, feats)
+    out = eng.forward(images.to(dev), ids, mask.sum(1), states=states.to(dev)).float().cpu()
+    tol = FP32_STAGE_TOL if dtype == torch.float32 else BF16_STAGE_TOL
+    assert rel_err(stage3, taps["vis_stage3"].permute(0, 2, 3, 1)) <= tol
+    assert rel_err(feats, taps["image_features"]) <= tol
+    if dtype == torch.float32:
+        assert (out - ref).abs().max().item() <= FP32_ACTION_TOL
+    else:
+        # One rounding more than the BatchNorm variant per attention block (the normalised row is a bf16 GEMM
+        # operand), and x - mean cancels leading bits of bf16 inputs: measured 2.7e-2 on this random-init tiny tower,
+        # against 1.0-1.6e-2 for the BatchNorm variant.  Stages are held to the common tolerance above.
+        assert rel_err(out, ref) <= 2 * BF16_ACTION_TOL
+
+
+def test_engine_io_normalization_fp32():
+    """fvla_set_io_normalization: state' = (state - mean)/(std + eps) in front of the head, action * std + mean behind
+    it (LeRobot MEAN_STD steps); None restores the identity."""
+    _need_gpu()
+    from oracle.fastvla_oracle import FastVLAOracle
+
+    arch, sd, hsd = tiny_weights(0)
+    images, states, ids, mask = make_inputs(3, 96, 96, 7, arch.text.vocab, TINY_HEAD["state_dim"], seed=9)
+    g = torch.Generator().manual_seed(1)
+    s_mean, s_std = torch.randn(6, generator=g), torch.rand(6, generator=g) + 0.5
+    a_mean, a_std = torch.randn(5, generator=g), torch.rand(5, generator=g) + 0.5
+    oracle = FastVLAOracle(arch, sd, hsd)
+    want = oracle.forward(images, (states - s_mean) / (s_std + 1e-8), ids, mask) * a_std + a_mean
+    plain = oracle.forward(images, states, ids, mask)
+    eng = make_engine(arch, sd, hsd, torch.float32)
+    dev = eng.device
+    eng.set_io_normalization(s_mean, s_std, a_mean, a_std)
+    got = eng.forward(images.to(dev), ids, mask.sum(1), states=states.to(dev)).float().cpu()
+    assert (got - want).abs().max() <= 1e-4, (got, want)
+    eng.set_io_normalization()
+    again = eng.forward(images.to(dev), ids, mask.sum(1), states=states.to(dev)).float().cpu()
+    assert (again - plain).abs().max() <= 1e-4
+    with pytest.raises(Exception, match="elements"):
+        eng.set_io_normalization(s_mean[:3], s_std[:3])
+
+
 def test_engine_mean_pool_fp32():
     _need_gpu()
     _run(torch.float32, "none", pool_mode="mean_pool")

@@ -30,6 +30,66 @@ def _policy(dtype, spec):
     return pol.cuda().eval()
 
 
+def _check_ill_conditioned_bf16(pol, images, states, tasks, actions, want):
+    """Raw 0..255 pixels drive the random-init tower's attention stages into near one-hot softmaxes: rounding only the
+    WEIGHTS to bf16 moves the fp32 oracle's actions by O(10 %) (asserted below, so the exemption cannot outlive its
+    reason).  The end-to-end figure therefore says nothing about the bf16 arithmetic; the case is pinned end to end in
+    fp32, and in bf16 every well-conditioned segment is held to the north_star tolerance separately:
+      (1) ingest + stem + the three RepMixer stages (before the first attention block) against the oracle taps,
+      (2) everything after the tower — projector, splice, Qwen2, pooling, head — against the oracle continued from the
+          ENGINE's own image features (oracle on bf16-rounded weights: what a bf16 run holds)."""
+    from helpers import tiny_weights
+    from oracle.fastvla_oracle import FastVLAOracle
+    from vla_fastvlm import _native as N
+
+    arch, sd, hsd = tiny_weights(0)
+    sd_q = {k: (v.bfloat16().float() if v.is_floating_point() and v.ndim >= 2 else v) for k, v in sd.items()}
+    be = pol.model.backbone
+    prompts = pol.processor.prepare_tasks(tasks, actions.shape[0])
+    ids, lens, _ = be._prompt_ids(prompts)
+    mask = (torch.arange(ids.shape[1])[None, :] < lens[:, None]).long()
+    taps, taps_q = {}, {}
+    ref = FastVLAOracle(arch, sd, hsd).forward(images, states, ids.long(), mask, taps=taps)
+    ref_q = FastVLAOracle(arch, sd_q, hsd).forward(images, states, ids.long(), mask, taps=taps_q)
+    assert np.abs(ref.numpy() - want).max() <= 1e-4                      # the oracle reproduces the reference golden
+    sensitivity = float((ref_q - ref).abs().max() / ref.abs().max())
+    assert sensitivity > 2e-2, f"case is no longer ill-conditioned ({sensitivity:.2e}): test it end to end instead"
+
+    eng = be.model.engine
+    dev, v, Bn = eng.device, arch.vision, images.shape[0]
+    bufs, side = {}, v.image_size // 4
+    bufs[N.TAP_STEM] = torch.zeros(Bn, side, side, v.dims[0], device=dev, dtype=torch.bfloat16)
+    for i, d in enumerate(v.dims):
+        bufs[N.TAP_VIS_STAGE0 + i] = torch.zeros(Bn, side, side, d, device=dev, dtype=torch.bfloat16)
+        side //= 2
+    bufs[N.TAP_IMAGE_FEATURES] = torch.zeros(Bn, v.num_tokens, v.out_channels, device=dev, dtype=torch.bfloat16)
+    for k, b in bufs.items():
+        eng.set_tap(k, b)
+    try:
+        with torch.no_grad():
+            got = pol.forward(images.to(dev), states.to(dev), tasks, device=dev).float().cpu()
+    finally:
+        for k in bufs:
+            eng.set_tap(k, None)
+    assert np.array_equal(got.numpy(), actions)                          # taps do not change the result
+
+    def rel(x, y):
+        return float((x.float().cpu() - y).abs().max() / y.abs().max())
+
+    seg1 = {"stem": rel(bufs[N.TAP_STEM], taps_q["stem"].permute(0, 2, 3, 1))}
+    for i, attn in enumerate(v.attention):
+        if attn:
+            break
+        seg1[f"vis_stage{i}"] = rel(bufs[N.TAP_VIS_STAGE0 + i], taps_q[f"vis_stage{i}"].permute(0, 2, 3, 1))
+    cont = FastVLAOracle(arch, sd_q, hsd).forward(images, states, ids.long(), mask,
+                                                  inject={"image_features": bufs[N.TAP_IMAGE_FEATURES]})
+    seg2 = float((got - cont).abs().max() / cont.abs().max())
+    print(f"uint8-valued bf16: oracle sensitivity to weight rounding {sensitivity:.2e}; pre-attention stages {seg1}; "
+          f"post-tower actions rel {seg2:.2e}")
+    assert all(e <= 6e-2 for e in seg1.values()), seg1                   # the tiny-arch bf16 stage tolerance
+    assert seg2 <= 2e-2, seg2
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 @pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
 def test_policy_forward_matches_reference_golden(name, dtype):
@@ -52,10 +112,7 @@ def test_policy_forward_matches_reference_golden(name, dtype):
     if dtype == "float32":
         assert np.abs(actions - want).max() <= 1e-3, np.abs(actions - want).max()
     elif name == "prefix_bhwc_uint8_values":
-        # Raw 0..255 pixels drive the random-init tower into near one-hot attention: merely rounding the
-        # WEIGHTS to bf16 moves the fp32 oracle's actions by ~33 % (measured), so no bf16 implementation can
-        # meet 2e-2 here.  The case is pinned in fp32 above; in bf16 only sanity is checked.
-        assert np.isfinite(actions).all() and np.abs(actions).max() < 10
+        _check_ill_conditioned_bf16(pol, images, states, tasks, actions, want)
     else:
         assert np.abs(actions - want).max() / np.abs(want).max() <= 2e-2, (actions, want)
 

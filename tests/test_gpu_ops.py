@@ -395,6 +395,18 @@ def test_rmsnorm(native, dtype, H):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Cc", [768, 1536, 128, 3072])
+def test_layernorm_rows(native, dtype, Cc):
+    """LayerNormChannel statistics (FastViTHD AttentionBlock.norm, affine folded elsewhere) vs torch layer_norm."""
+    dev = _dev()
+    g = torch.Generator().manual_seed(5 + Cc)
+    x = (torch.randn(517, Cc, generator=g) * 2 + 0.7).to(dev).to(dtype)
+    out = native.op_layernorm_rows(x, 1e-5)
+    ref = torch.nn.functional.layer_norm(x.float(), (Cc,), None, None, 1e-5)
+    _close(out, ref, BF16_TOL if dtype == torch.bfloat16 else F32_TOL, "layernorm_rows")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,HW,Cc,Cr", [(3, 256, 512, 32), (2, 256, 3072, 192), (9, 64, 104, 8)])
 def test_se_gelu(native, dtype, B, HW, Cc, Cr):
     dev = _dev()

@@ -97,6 +97,62 @@ def test_plugin_select_action_and_forward():
     assert post(pred).device.type == "cpu"
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [("float32", 2e-5), ("bfloat16", 2e-2)])
+def test_fused_io_normalization_and_uint8_host_ingest(dtype, tol):
+    """Row f1: raw uint8 HWC camera frames + raw state in HOST memory through the fused pipelines (statistics applied
+    inside the head kernel, frames scaled inside the ingest kernel, staged copy on a side stream) give the actions the
+    reference-shaped pipelines give on float [0,1] CHW device tensors (reference lerobot_fastvla/processor_fastvla.py:30-48)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from vla_fastvlm.lerobot_fastvla import FastVLAConfig, FastVLAPolicy, make_fastvla_pre_post_processors
+
+    inp, outp = _features(n_cam=1)
+    common = dict(input_features=inp, output_features=outp, device="cuda", vlm_model_name="synthetic:tiny",
+                  hidden_dim=TINY_HEAD["hidden_dim"], fusion_dim=TINY_HEAD["fusion_dim"], image_token_mode="prefix",
+                  compute_dtype=dtype)
+    plain_cfg = FastVLAConfig(**common)
+    fused_cfg = FastVLAConfig(fuse_io_normalization=True, image_input_scale=1.0 / 255.0, **common)
+    plain = FastVLAPolicy(plain_cfg).cuda()
+    fused = FastVLAPolicy(fused_cfg).cuda()
+    fused.load_state_dict(plain.state_dict(), strict=True)
+    g = torch.Generator().manual_seed(7)
+    stats = {"observation.state": {"mean": torch.randn(6, generator=g), "std": torch.rand(6, generator=g) + 0.5},
+             "action": {"mean": torch.randn(5, generator=g), "std": torch.rand(5, generator=g) + 0.5}}
+    B = 3
+    frames = torch.randint(0, 256, (B, 96, 128, 3), generator=g, dtype=torch.uint8).pin_memory()   # camera: HWC uint8
+    state = (torch.randn(B, 6, generator=g) * 2 + 1).pin_memory()
+    pre_p, post_p = make_fastvla_pre_post_processors(plain_cfg, dataset_stats=stats)
+    pre_f, post_f = make_fastvla_pre_post_processors(fused_cfg, dataset_stats=stats)
+    want = post_p(plain.select_action(pre_p({"observation.images.cam0": frames.permute(0, 3, 1, 2).float() / 255.0,
+                                              "observation.state": state.clone(), "task": ["push the block"]})))
+    got = post_f(fused.select_action(pre_f({"observation.images.cam0": frames, "observation.state": state,
+                                             "task": ["push the block"]})))
+    assert got.device.type == "cpu" and want.device.type == "cpu" and got.shape == (B, 5)
+    assert fused._stager is not None and fused._stager.h2d_bytes == frames.numel() + state.numel() * 4
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err <= tol, (err, got, want)
+    # a second call with new observations reuses the staging slots and the pushed statistics
+    frames2 = torch.randint(0, 256, (B, 96, 128, 3), generator=g, dtype=torch.uint8).pin_memory()
+    fused.reset(); plain.reset()
+    want2 = post_p(plain.select_action(pre_p({"observation.images.cam0": frames2.permute(0, 3, 1, 2).float() / 255.0,
+                                               "observation.state": state.clone(), "task": ["push the block"]})))
+    got2 = post_f(fused.select_action(pre_f({"observation.images.cam0": frames2, "observation.state": state,
+                                              "task": ["push the block"]})))
+    assert float((got2 - want2).abs().max() / want2.abs().max()) <= tol and not torch.allclose(got2, got)
+    # training through the fused configuration: the loss is the MSE in NORMALISED action space, as with the plain pipelines
+    fused.train(); plain.train()
+    act = torch.randn(B, 1, 5, generator=g)
+    torch.manual_seed(0)
+    loss_p, _ = plain.forward(pre_p({"observation.images.cam0": frames.permute(0, 3, 1, 2).float() / 255.0,
+                                     "observation.state": state.clone(), "task": ["push the block"], "action": act}))
+    torch.manual_seed(0)
+    loss_f, _ = fused.forward(pre_f({"observation.images.cam0": frames, "observation.state": state,
+                                     "task": ["push the block"], "action": act}))
+    assert abs(float(loss_p) - float(loss_f)) <= (1e-4 if dtype == "float32" else 5e-2) * max(1.0, float(loss_p))
+
+
+@pytest.mark.gpu
 def test_training_step_updates_head_and_engine():
     """The data-parallel training step (world size 1 here): frozen backbone in the engine, head through autograd,
     gradients accumulated into the flat all-reduce buffer, AdamW on the head only — the loss falls, the backbone's

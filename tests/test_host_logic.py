@@ -58,6 +58,21 @@ def test_arch_presets_and_flop_model():
     assert b.text == PRESETS["fastvlm-1.5b"].text and b.vision.image_size == 1024
 
 
+def test_oracle_attention_norm_variants():
+    """The oracle's two restatements of AttentionBlock.norm: LayerNormChannel equals torch's layer_norm over the channel
+    axis; the key set selects the variant (SURVEY App. A leaves the layer type unverified)."""
+    from oracle.fastvla_oracle import _attn_norm, _bn, _ln_channel
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 24, 5, 7, generator=g) * 2 + 1
+    sd = {"n.weight": torch.rand(24, generator=g) + 0.5, "n.bias": torch.randn(24, generator=g)}
+    want = torch.nn.functional.layer_norm(x.permute(0, 2, 3, 1), (24,), sd["n.weight"], sd["n.bias"], 1e-5)
+    assert torch.allclose(_ln_channel(sd, "n", x), want.permute(0, 3, 1, 2), atol=1e-5)
+    assert torch.equal(_attn_norm(sd, "n", x), _ln_channel(sd, "n", x))
+    sd.update({"n.running_mean": torch.randn(24, generator=g), "n.running_var": torch.rand(24, generator=g) + 0.5})
+    assert torch.equal(_attn_norm(sd, "n", x), _bn(sd, "n", x))
+
+
 def test_shard_range_partitions_the_batch():
     sys.path.insert(0, str(ROOT))
     import bench

@@ -300,11 +300,7 @@ template <int HD, bool CAUSAL, bool ROPE>
 int launch_flash(const AttnArgs& a, cudaStream_t stream) {
   auto kfn = flash_attn_bf16_kernel<HD, CAUSAL, ROPE>;
   constexpr int SMEM = (BQ + 2 * BKV) * (HD + 8) * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), SMEM)) return rc;
   dim3 grid(ceil_div(a.N, BQ), a.heads_q, a.B);
   const float sl2 = a.scale * 1.4426950408889634f;
   kfn<<<grid, 128, SMEM, stream>>>(
@@ -321,7 +317,7 @@ int launch_simt(const AttnArgs& a, cudaStream_t stream) {
   const int smem = 4 * (a.head_dim + a.N) * static_cast<int>(sizeof(float));
   FVLA_REQUIRE(smem <= 200 * 1024, "attention_simt: sequence too long for the score buffer");
   if (smem > 48 * 1024)
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), smem)) return rc;
   dim3 grid(ceil_div(a.N, 4), a.heads_q, a.B);
   kfn<<<grid, 128, smem, stream>>>(static_cast<const T*>(a.q), static_cast<const T*>(a.k),
                                    static_cast<const T*>(a.v), a.ld_qkv, static_cast<T*>(a.o),

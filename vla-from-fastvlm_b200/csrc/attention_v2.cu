@@ -410,11 +410,7 @@ int launch_gqa(const AttnArgs& a, cudaStream_t stream) {
   auto kfn = flash_attn_gqa_kernel<HD>;
   const int group = a.heads_q / a.heads_kv;
   const int smem = (4 * BKV2 + 8 * 16) * (HD + 8) * 2;  // Q sized for the largest group
-  static bool attr_set = false;
-  if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), smem)) return rc;
   dim3 grid(ceil_div(a.N, 16), a.heads_kv, a.B);
   kfn<<<grid, 32 * group, smem, stream>>>(static_cast<const __nv_bfloat16*>(a.q), static_cast<const __nv_bfloat16*>(a.k),
                                           static_cast<const __nv_bfloat16*>(a.v), a.ld_qkv, static_cast<__nv_bfloat16*>(a.o),
@@ -428,11 +424,7 @@ int launch_v2(const AttnArgs& a, cudaStream_t stream) {
   auto kfn = flash_attn_v2_kernel<HD, CAUSAL, NWARPS>;
   constexpr int BQ2 = 16 * NWARPS;
   constexpr int SMEM = (BQ2 + 4 * BKV2) * (HD + 8) * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), SMEM)) return rc;
   dim3 grid(ceil_div(a.N, BQ2), a.heads_q, a.B);
   kfn<<<grid, 32 * NWARPS, SMEM, stream>>>(static_cast<const __nv_bfloat16*>(a.q), static_cast<const __nv_bfloat16*>(a.k),
                                    static_cast<const __nv_bfloat16*>(a.v), a.ld_qkv,

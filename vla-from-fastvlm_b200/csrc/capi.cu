@@ -3,7 +3,10 @@
 #include "common.cuh"
 
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
+#include <utility>
 
 namespace fvla {
 
@@ -22,6 +25,20 @@ int num_sms() {
       cached = 148;
   }
   return cached;
+}
+
+int ensure_dyn_smem(const void* fn, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> raised;
+  int dev = 0;
+  FVLA_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_pair(fn, dev);
+  auto it = raised.find(key);
+  if (it != raised.end() && it->second >= bytes) return 0;
+  FVLA_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  raised[key] = bytes;
+  return 0;
 }
 
 }  // namespace fvla
@@ -116,6 +133,11 @@ int fvla_set_tap(fvla_engine* e, int32_t stage, void* dst, int64_t cap) {
   return e->impl.set_tap(stage, dst, cap);
 }
 int fvla_merged_len(fvla_engine* e) { return e ? e->impl.merged_len : 0; }
+int fvla_set_io_normalization(fvla_engine* e, const float* state_mean, const float* state_inv_std,
+                              const float* action_scale, const float* action_shift) {
+  if (e == nullptr) { set_error("null engine"); return 2; }
+  return e->impl.set_io_normalization(state_mean, state_inv_std, action_scale, action_shift);
+}
 int fvla_set_profile(fvla_engine* e, int32_t on) {
   if (e == nullptr) { set_error("null engine"); return 2; }
   e->impl.set_profile(on != 0);
@@ -195,6 +217,10 @@ int fvla_op_attention(int32_t dtype, int32_t impl, const void* q, const void* k,
 int fvla_op_rmsnorm(int32_t dtype, const void* x, const float* weight, void* out, int32_t rows,
                     int32_t H, float eps, void* stream) {
   return fvla::rmsnorm(dtype, x, weight, out, rows, H, eps, static_cast<cudaStream_t>(stream));
+}
+
+int fvla_op_layernorm_rows(int32_t dtype, const void* x, void* out, int32_t rows, int32_t C, float eps, void* stream) {
+  return fvla::layernorm_rows(dtype, x, out, rows, C, eps, static_cast<cudaStream_t>(stream));
 }
 
 int fvla_op_ffn_fused(const void* x, const void* w1_half, const float* b1_half, const void* w2,

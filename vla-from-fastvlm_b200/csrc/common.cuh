@@ -146,5 +146,8 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 int num_sms();  // cached SM count of the current device
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): raised once per pair (a process may hold
+// engines on several GPUs), thread-safe, ~50 ns on the repeat path
+int ensure_dyn_smem(const void* fn, int bytes);
 
 }  // namespace fvla

@@ -261,11 +261,7 @@ int launch(const void* in, const float* w_packed, const float* bias, void* out, 
            cudaStream_t stream) {
   using G = Geo<CB>;
   auto kfn = dwconv3_tma_kernel<CB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_B));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), G::SMEM_B)) return rc;
   CUtensorMap ti;
   if (int rc = make_tmap<CB>(&ti, in, B, H, W, C)) return rc;
   const int tiles_x = W / G::TW, tiles_y = H / TH, n_cblk = C / CB;

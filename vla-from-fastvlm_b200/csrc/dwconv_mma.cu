@@ -351,11 +351,7 @@ int launch_mma(const void* in, const uint32_t* wtab, const float* bias, void* ou
                cudaStream_t stream) {
   using G = Geo<NB>;
   auto kfn = dwconv7_mma_kernel<NB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_B));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), G::SMEM_B)) return rc;
   CUtensorMap ti;
   if (int rc = make_tmap_nhwc(&ti, in, B, H, W, C, G::IW, 2)) return rc;
   const int tiles_x = W / G::TW, tiles_y = H / TH, n_cblk = C / CB;

@@ -205,11 +205,7 @@ int launch_tiled_h(const void* in, const float* w, const float* bias, void* out,
   using G = TileGeom<K>;
   auto kfn = dwconv_tiled_h_kernel<K>;
   constexpr int SMEM = G::IN_BYTES + K * K * (CB / 2) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), SMEM)) return rc;
   dim3 grid((W / G::TW) * (H / TH), C / CB, B);
   kfn<<<grid, 256, SMEM, stream>>>(static_cast<const __nv_bfloat16*>(in), w, bias,
                                    static_cast<__nv_bfloat16*>(out), H, W, C, act);
@@ -372,11 +368,7 @@ bool dwconv_s2m2_tiled_supported(int dtype, int H, int W, int Cin, int mult, int
 
 int dwconv_s2m2_tiled(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int Cin,
                       int act, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(dwconv7_s2m2_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(dwconv7_s2m2_tiled_kernel), S2_SMEM)) return rc;
   dim3 grid((W / 2 / S2_TWO) * (H / 2 / S2_THO), 2 * Cin / S2_CBO, B);
   dwconv7_s2m2_tiled_kernel<<<grid, 256, S2_SMEM, stream>>>(static_cast<const __nv_bfloat16*>(in), w, bias,
                                                              static_cast<__nv_bfloat16*>(out), H, W, Cin, act);

@@ -18,6 +18,7 @@ const char* kVis = "backbone.model.model.vision_tower.vision_tower.model.";
 const char* kProj = "backbone.model.model.mm_projector.";
 const char* kLlm = "backbone.model.model.";
 constexpr float kBnEps = 1e-5f;  // torch.nn.BatchNorm2d default
+constexpr float kLnChannelEps = 1e-5f;  // LayerNormChannel default [EXT mci.py]
 
 std::string S(const char* p, const std::string& rest) { return std::string(p) + rest; }
 }  // namespace
@@ -31,6 +32,10 @@ Engine::~Engine() {
   for (auto& kv : ws_.bufs) cudaFree(kv.second.first);
   for (auto& p : prof_) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
   for (auto e : ev_pool_) cudaEventDestroy(e);
+  for (auto& hs : host_ring_) {
+    if (hs.ev != nullptr) cudaEventDestroy(hs.ev);
+    if (hs.p != nullptr) cudaFreeHost(hs.p);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -148,7 +153,12 @@ std::vector<std::string> Engine::required_names() const {
     for (int j = 0; j < cfg.vis_layers[i]; ++j) {
       const std::string b = S(kVis, "network." + std::to_string(st) + "." + std::to_string(j));
       if (cfg.vis_attention[i]) {
-        bn(b + ".norm");
+        // pre-attention norm: BatchNorm2d (running stats present) or LayerNormChannel (weight/bias only) — the
+        // checkpoint's key set decides (pack_vision)
+        if (host_.find(b + ".norm.running_mean") != host_.end() || host_.find(b + ".norm.running_var") != host_.end())
+          bn(b + ".norm");
+        else
+          wb(b + ".norm");
         r.push_back(b + ".token_mixer.qkv.weight");
         wb(b + ".token_mixer.proj");
         r.push_back(b + ".layer_scale_1");
@@ -403,19 +413,29 @@ int Engine::pack_vision() {
       if (cfg.vis_attention[i]) {
         blk.attn = true;
         FVLA_REQUIRE(d % cfg.vis_head_dim == 0, "attention stage width must be a multiple of head_dim");
-        const HostTensor *nw, *nb, *nm, *nv, *qw, *pw, *pb, *ls1, *ls2;
+        const HostTensor *nw, *nb, *nm = nullptr, *nv = nullptr, *qw, *pw, *pb, *ls1, *ls2;
         if (int rc = need(base + ".norm.weight", &nw, {d})) return rc;
         if (int rc = need(base + ".norm.bias", &nb, {d})) return rc;
-        if (int rc = need(base + ".norm.running_mean", &nm, {d})) return rc;
-        if (int rc = need(base + ".norm.running_var", &nv, {d})) return rc;
+        // BatchNorm2d carries running statistics and folds into qkv completely; LayerNormChannel [EXT mci.py]
+        // (per-token statistics over the channels) keeps a run-time normalisation kernel and folds only its affine
+        blk.attn_layernorm = find(base + ".norm.running_mean") == nullptr;
+        if (!blk.attn_layernorm) {
+          if (int rc = need(base + ".norm.running_mean", &nm, {d})) return rc;
+          if (int rc = need(base + ".norm.running_var", &nv, {d})) return rc;
+        }
         if (int rc = need(base + ".token_mixer.qkv.weight", &qw, {3 * d, d})) return rc;
         if (int rc = need(base + ".token_mixer.proj.weight", &pw, {d, d})) return rc;
         if (int rc = need(base + ".token_mixer.proj.bias", &pb, {d})) return rc;
         if (int rc = need(base + ".layer_scale_1", &ls1, {d})) return rc;
         if (int rc = need(base + ".layer_scale_2", &ls2, {d})) return rc;
         std::vector<double> s, t;
-        bn_affine(*nw, *nb, *nm, *nv, &s, &t);
-        // qkv(BN(x)) = (W diag(s)) x + W t
+        if (blk.attn_layernorm) {
+          s.assign(nw->data.begin(), nw->data.end());
+          t.assign(nb->data.begin(), nb->data.end());
+        } else {
+          bn_affine(*nw, *nb, *nm, *nv, &s, &t);
+        }
+        // qkv(norm(x)) = (W diag(s)) n + W t   (n = x for BatchNorm, the normalised row for LayerNormChannel)
         std::vector<float> qf(qw->data.size()), qb(static_cast<size_t>(3) * d);
         for (int n = 0; n < 3 * d; ++n) {
           double acc = 0.0;
@@ -549,6 +569,16 @@ int Engine::pack_head() {
       {"action_head.weight", &head_.w_act, static_cast<int64_t>(A) * F, true},
       {"action_head.bias", reinterpret_cast<const void**>(&head_.b_act), A, false},
   };
+  {
+    // LeRobot (un)normaliser fused into the head: identity until fvla_set_io_normalization
+    std::vector<float> ident(static_cast<size_t>(2 * Sd + 2 * A), 0.f);
+    for (int i = 0; i < Sd; ++i) ident[Sd + i] = 1.f;
+    for (int i = 0; i < A; ++i) ident[2 * Sd + i] = 1.f;
+    io_norm_ = upload_f32(ident);
+    FVLA_REQUIRE(io_norm_ != nullptr, "cudaMalloc failed (io normalisation)");
+    head_.st_mean = io_norm_; head_.st_inv_std = io_norm_ + Sd;
+    head_.act_scale = io_norm_ + 2 * Sd; head_.act_shift = io_norm_ + 2 * Sd + A;
+  }
   for (const Slot& sl : slots) {
     const HostTensor* t;
     if (int rc = need(sl.name, &t, {sl.n})) return rc;
@@ -576,6 +606,24 @@ int Engine::update_head_tensor(const std::string& name, const HostTensor& t) {
   } else {
     FVLA_CUDA_CHECK(cudaMemcpy(it->second.ptr, t.data.data(), t.data.size() * 4, cudaMemcpyHostToDevice));
   }
+  return 0;
+}
+
+int Engine::set_io_normalization(const float* state_mean, const float* state_inv_std, const float* action_scale,
+                                 const float* action_shift) {
+  FVLA_REQUIRE(finalized_ && io_norm_ != nullptr, "set_io_normalization: engine has no finalized action head");
+  const int Sd = cfg.state_dim, A = cfg.action_dim;
+  std::vector<float> v(static_cast<size_t>(2 * Sd + 2 * A), 0.f);
+  for (int i = 0; i < Sd; ++i) {
+    v[i] = state_mean ? state_mean[i] : 0.f;
+    v[Sd + i] = state_inv_std ? state_inv_std[i] : 1.f;
+  }
+  for (int i = 0; i < A; ++i) {
+    v[2 * Sd + i] = action_scale ? action_scale[i] : 1.f;
+    v[2 * Sd + A + i] = action_shift ? action_shift[i] : 0.f;
+  }
+  // in place: captured graphs keep pointing at the same buffer
+  FVLA_CUDA_CHECK(cudaMemcpy(io_norm_, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -886,7 +934,15 @@ int Engine::vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats
         std::swap(X, Y);
       } else {
         // AttentionBlock: x = x + ls1 * MHSA(BN(x)); x = x + ls2 * ConvFFN(x)
-        if (int rc = run_gemm(blk.qkv, X, Hb, M, ACT_NONE, nullptr, false, s)) return rc;
+        const char* qkv_in = X;
+        if (blk.attn_layernorm) {
+          ++launches;
+          prof_begin(s);
+          if (int rc = layernorm_rows(cfg.dtype, X, Y, M, d, kLnChannelEps, s)) return rc;
+          prof_end("vis.layernorm C" + std::to_string(d), 0.0, 2.0 * M * static_cast<double>(d) * e, s);
+          qkv_in = Y;
+        }
+        if (int rc = run_gemm(blk.qkv, qkv_in, Hb, M, ACT_NONE, nullptr, false, s)) return rc;
         AttnArgs at;
         at.q = Hb; at.k = Hb + static_cast<size_t>(d) * e; at.v = Hb + static_cast<size_t>(2 * d) * e;
         at.ld_qkv = 3 * d; at.o = Z; at.ld_o = d;
@@ -945,7 +1001,22 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
     Tm = std::max(Tm, mlen[b]);
   }
   merged_len = Tm;
-  std::vector<int> plan(static_cast<size_t>(B) * Tm, -1), pidx(B), lens(B);
+  // Host staging of the splice plan: a ring of PINNED buffers, each guarded by an event, so the upload is a true
+  // asynchronous copy (a pageable source above the driver's inline limit makes cudaMemcpyAsync stage + wait on the
+  // host, which would serialise the caller's launch-ahead with the GPU).
+  const size_t n_plan = static_cast<size_t>(B) * Tm, n_ints = n_plan + 2 * static_cast<size_t>(B);
+  HostStage& hs = host_ring_[host_ring_next_];
+  host_ring_next_ = (host_ring_next_ + 1) % kHostRing;
+  if (hs.ev == nullptr) FVLA_CUDA_CHECK(cudaEventCreateWithFlags(&hs.ev, cudaEventDisableTiming));
+  else FVLA_CUDA_CHECK(cudaEventSynchronize(hs.ev));  // the copy that last read this slot has completed
+  if (hs.cap < n_ints) {
+    if (hs.p != nullptr) FVLA_CUDA_CHECK(cudaFreeHost(hs.p));
+    hs.p = nullptr; hs.cap = 0;
+    FVLA_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&hs.p), n_ints * 4 + 64));
+    hs.cap = n_ints;
+  }
+  int* plan = hs.p; int* pidx = hs.p + n_plan; int* lens = pidx + B;
+  std::fill(plan, plan + n_plan, -1);
   for (int b = 0; b < B; ++b) {
     int pos = 0;
     for (int t = 0; t < a.text_len[b]; ++t) {
@@ -965,9 +1036,10 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
   int* d_plan = static_cast<int*>(ws_.bufs["plan"].first);
   int* d_pidx = static_cast<int*>(ws_.bufs["pool_idx"].first);
   int* d_lens = static_cast<int*>(ws_.bufs["lens"].first);
-  FVLA_CUDA_CHECK(cudaMemcpyAsync(d_plan, plan.data(), plan.size() * 4, cudaMemcpyHostToDevice, s));
-  FVLA_CUDA_CHECK(cudaMemcpyAsync(d_pidx, pidx.data(), pidx.size() * 4, cudaMemcpyHostToDevice, s));
-  FVLA_CUDA_CHECK(cudaMemcpyAsync(d_lens, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice, s));
+  FVLA_CUDA_CHECK(cudaMemcpyAsync(d_plan, plan, n_plan * 4, cudaMemcpyHostToDevice, s));
+  FVLA_CUDA_CHECK(cudaMemcpyAsync(d_pidx, pidx, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, s));
+  FVLA_CUDA_CHECK(cudaMemcpyAsync(d_lens, lens, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, s));
+  FVLA_CUDA_CHECK(cudaEventRecord(hs.ev, s));
 
   // ---- CUDA-graph replay for small batches (the b=1 select_action latency is launch-bound: ~390 launches) ----
   static const bool graphs_on = std::getenv("FVLA_DISABLE_GRAPHS") == nullptr;

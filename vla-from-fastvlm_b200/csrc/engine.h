@@ -31,6 +31,7 @@ struct DwW {  // packed depthwise / grouped conv
 };
 struct VisBlock {
   bool attn = false;
+  bool attn_layernorm = false;  // pre-attention norm is LayerNormChannel (run-time statistics) instead of BatchNorm2d
   DwW mixer;           // RepMixer reparam 3x3 (repmixer blocks only)
   GemmW qkv, proj;     // attention blocks only (BN folded into qkv, layer_scale_1 into proj)
   DwW ffn_dw;          // ConvFFN 7x7 with BN folded
@@ -62,6 +63,9 @@ class Engine {
   int reserve(int B, int n_tokens);
   int forward(const fvla_forward_args& a, cudaStream_t stream);
   int set_tap(int stage, void* dst, int64_t cap);
+  // host fp32 vectors ([state_dim] x2, [action_dim] x2), any may be null (= identity for that part)
+  int set_io_normalization(const float* state_mean, const float* state_inv_std, const float* action_scale,
+                           const float* action_shift);
   // per-launch CUDA-event profiling (off by default; adds two event records per kernel)
   void set_profile(bool on) { profile_ = on; }
   int profile_report(std::string* csv);  // syncs, aggregates by label, clears the samples
@@ -129,6 +133,12 @@ class Engine {
   float* final_norm_ = nullptr;
   float* rope_cos_ = nullptr; float* rope_sin_ = nullptr; int rope_len_ = 0;
   HeadWeights head_{};
+  float* io_norm_ = nullptr;  // [S mean | S inv_std | A scale | A shift]
+
+  struct HostStage { int* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; };
+  static constexpr int kHostRing = 4;
+  HostStage host_ring_[kHostRing];
+  int host_ring_next_ = 0;
 
   Workspace ws_;
   std::map<int, std::pair<void*, int64_t>> taps_;

@@ -117,5 +117,22 @@ __device__ __forceinline__ uint32_t gelu_half_f16x2(float h_lo, float h_hi) {
   return o;
 }
 
+// same, with the (pre-halved) bias added as a packed half pair after the conversion: 1 HADD2 per pair instead of 2 FADD
+__device__ __forceinline__ uint32_t gelu_half_f16x2_b(float h_lo, float h_hi, uint32_t bias2) {
+  uint32_t h, u, q, a, t, o;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(h_hi), "f"(h_lo));
+  asm("add.rn.f16x2 %0, %0, %1;" : "+r"(h) : "r"(bias2));
+  const uint32_t c0 = h2_splat(1.594015768f), c1 = h2_splat(2.96045168e-01f), c2 = h2_splat(-1.124853725e-02f);
+  const uint32_t k16 = h2_splat(16.0f);
+  asm("mul.rn.f16x2 %0, %1, %1;" : "=r"(u) : "r"(h));
+  asm("min.f16x2 %0, %1, %2;" : "=r"(u) : "r"(u), "r"(k16));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(q) : "r"(u), "r"(c2), "r"(c1));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(q) : "r"(u), "r"(q), "r"(c0));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(a) : "r"(h), "r"(q));
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(a));
+  asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(o) : "r"(h), "r"(t));
+  return o;
+}
+
 }  // namespace epi
 }  // namespace fvla

@@ -25,6 +25,8 @@
 #include "ptx_sm100.cuh"
 #include "tma_host.h"
 
+#include <cstdlib>
+
 namespace fvla {
 namespace {
 using namespace epi;
@@ -48,7 +50,7 @@ template <int C> struct FfnCfg {
   static constexpr int NOSUB = (C + 63) / 64;                // 64-column output sub-tiles
   static constexpr int BAR_BYTES = 512;
   static constexpr int MAX_HIDDEN = 4 * C;                   // b1 is kept in shared memory (ConvFFN ratio 4)
-  static constexpr int BIAS_BYTES = (MAX_HIDDEN + C) * 4;
+  static constexpr int BIAS_BYTES = (MAX_HIDDEN + C) * 4 + MAX_HIDDEN * 2;  // b1 fp32, b2 fp32, b1 as packed halves
   static constexpr int SMEM_BYTES = X_BYTES + STAGES * STAGE_BYTES + 2 * H_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
   static_assert(C % 32 == 0 && C <= 192, "O accumulators must fit TMEM columns [0, 256)");
   static_assert(2 * H_BYTES >= EPI_WARPS * 4096, "H buffers double as the output staging slabs");
@@ -63,7 +65,10 @@ struct FfnParams {
   int ldr;
 };
 
-template <int C>
+// TEAMS: the 16 epilogue warps work as two teams of 8 (team = chunk parity = S/H buffer): each warp evaluates the GELU
+// of 32 rows x 64 columns of every OTHER chunk, so the four warps of a scheduler are spread over two chunks in
+// different phases (TMEM load / math / barrier hand-off) instead of marching through one chunk in lock step.
+template <int C, bool TEAMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FFN_THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
                  const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_out,
@@ -89,7 +94,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   // top long-scoreboard stall of the epilogue)
   float* s_b1 = reinterpret_cast<float*>(smem_ffn + (bar_base - ptx::smem_u32(smem_ffn)) + Cfg::BAR_BYTES);
   float* s_b2 = s_b1 + Cfg::MAX_HIDDEN;
+  uint32_t* s_b1h = reinterpret_cast<uint32_t*>(s_b2 + C);  // b1 as f16x2 pairs (TEAMS epilogue adds the bias in half)
   for (int i = threadIdx.x; i < p.hidden; i += FFN_THREADS) s_b1[i] = p.b1[i];
+  for (int i = threadIdx.x; i < p.hidden / 2; i += FFN_THREADS) {
+    uint32_t pk;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(p.b1[2 * i + 1]), "f"(p.b1[2 * i]));
+    s_b1h[i] = pk;
+  }
   for (int i = threadIdx.x; i < C; i += FFN_THREADS) s_b2[i] = p.b2[i];
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,8 +126,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     ptx::mbar_init(xempty, 1);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(sfull(b), 1);
-      ptx::mbar_init(sempty(b), 2 * EPI_WARPS);
-      ptx::mbar_init(hfull(b), 2 * EPI_WARPS);
+      ptx::mbar_init(sempty(b), TEAMS ? EPI_WARPS : 2 * EPI_WARPS);
+      ptx::mbar_init(hfull(b), TEAMS ? EPI_WARPS : 2 * EPI_WARPS);
       ptx::mbar_init(hempty(b), 1);
     }
     ptx::mbar_init(ofull, 1);
@@ -274,38 +285,83 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     uint32_t g = 0, t = 0;
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++t) {
       const int m0 = tile * FPAIR_M + static_cast<int>(cta_rank) * FM;
+      if constexpr (TEAMS) {
+        const uint32_t team = static_cast<uint32_t>(grp >> 1), half = static_cast<uint32_t>(grp & 1);
+        for (int j = 0; j < nch; ++j, ++g) {
+          const uint32_t b = g & 1u, use = (g >> 1) & 1u;
+          if (b != team) continue;
+          ptx::mbar_wait(sfull(b), use);
+          ptx::tc_fence_after();
+          const uint32_t hrow = smem_h + b * Cfg::H_BYTES + half * PANEL_BYTES + row * 128;
+          const uint32_t* b1h = s_b1h + (j * HC + half * 64) / 2;
+#pragma unroll
+          for (int hp = 0; hp < 2; ++hp) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(lane_base + (b ? TMEM_S1 : TMEM_S0) + half * 64u + static_cast<uint32_t>(hp * 32), r);
+            ptx::tmem_ld_wait();
+            if (hp == 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_cluster(b ? sempty_leader1 : sempty_leader0);  // S[b] is in registers
+            } else {
+              ptx::mbar_wait(hempty(b), use ^ 1u);  // GEMM2 two chunks ago has finished reading H[b]
+            }
+            uint32_t hq[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 b4 = reinterpret_cast<const uint4*>(b1h + hp * 16)[q];
+              hq[4 * q] = gelu_half_f16x2_b(__uint_as_float(r[8 * q]), __uint_as_float(r[8 * q + 1]), b4.x);
+              hq[4 * q + 1] = gelu_half_f16x2_b(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3]), b4.y);
+              hq[4 * q + 2] = gelu_half_f16x2_b(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5]), b4.z);
+              hq[4 * q + 3] = gelu_half_f16x2_b(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7]), b4.w);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int chunk = hp * 4 + c;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + ((chunk ^ (row & 7)) << 4)),
+                           "r"(hq[4 * c]), "r"(hq[4 * c + 1]), "r"(hq[4 * c + 2]), "r"(hq[4 * c + 3])
+                           : "memory");
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();  // generic-proxy writes of H -> visible to the tensor core's async reads
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(b ? hfull_leader1 : hfull_leader0);
+        }
+      } else {
       for (int j = 0; j < nch; ++j, ++g) {
-        const uint32_t b = g & 1u, use = (g >> 1) & 1u;
-        ptx::mbar_wait(sfull(b), use);
-        ptx::tc_fence_after();
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(lane_base + (b ? TMEM_S1 : TMEM_S0) + static_cast<uint32_t>(grp * 32), r);
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(b ? sempty_leader1 : sempty_leader0);  // S[b] is in registers
-        ptx::mbar_wait(hempty(b), use ^ 1u);  // GEMM2 two chunks ago has finished reading H[b]
-        const float* b1 = s_b1 + j * HC + grp * 32;
-        uint32_t hq[16];  // 32 GELU outputs as fp16 pairs
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 b4 = reinterpret_cast<const float4*>(b1)[q];
-          hq[2 * q] = gelu_half_f16x2(__uint_as_float(r[4 * q]) + b4.x, __uint_as_float(r[4 * q + 1]) + b4.y);
-          hq[2 * q + 1] = gelu_half_f16x2(__uint_as_float(r[4 * q + 2]) + b4.z, __uint_as_float(r[4 * q + 3]) + b4.w);
+          const uint32_t b = g & 1u, use = (g >> 1) & 1u;
+          ptx::mbar_wait(sfull(b), use);
+          ptx::tc_fence_after();
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(lane_base + (b ? TMEM_S1 : TMEM_S0) + static_cast<uint32_t>(grp * 32), r);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(b ? sempty_leader1 : sempty_leader0);  // S[b] is in registers
+          ptx::mbar_wait(hempty(b), use ^ 1u);  // GEMM2 two chunks ago has finished reading H[b]
+          const float* b1 = s_b1 + j * HC + grp * 32;
+          uint32_t hq[16];  // 32 GELU outputs as fp16 pairs
+  #pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b4 = reinterpret_cast<const float4*>(b1)[q];
+            hq[2 * q] = gelu_half_f16x2(__uint_as_float(r[4 * q]) + b4.x, __uint_as_float(r[4 * q + 1]) + b4.y);
+            hq[2 * q + 1] = gelu_half_f16x2(__uint_as_float(r[4 * q + 2]) + b4.z, __uint_as_float(r[4 * q + 3]) + b4.w);
+          }
+          // H[b]: two K-major panels of 64 columns; this warp's 32 columns are chunks 4*(grp&1) .. +3 of panel grp>>1
+          const uint32_t hrow = smem_h + b * Cfg::H_BYTES + static_cast<uint32_t>(grp >> 1) * PANEL_BYTES + row * 128;
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int chunk = (grp & 1) * 4 + c;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + ((chunk ^ (row & 7)) << 4)),
+                         "r"(hq[4 * c]), "r"(hq[4 * c + 1]), "r"(hq[4 * c + 2]), "r"(hq[4 * c + 3])
+                         : "memory");
+          }
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();  // generic-proxy writes of H -> visible to the tensor core's async reads
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(b ? hfull_leader1 : hfull_leader0);
         }
-        // H[b]: two K-major panels of 64 columns; this warp's 32 columns are chunks 4*(grp&1) .. +3 of panel grp>>1
-        const uint32_t hrow = smem_h + b * Cfg::H_BYTES + static_cast<uint32_t>(grp >> 1) * PANEL_BYTES + row * 128;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int chunk = (grp & 1) * 4 + c;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + ((chunk ^ (row & 7)) << 4)),
-                       "r"(hq[4 * c]), "r"(hq[4 * c + 1]), "r"(hq[4 * c + 2]), "r"(hq[4 * c + 3])
-                       : "memory");
-        }
-        ptx::tc_fence_before();
-        ptx::fence_proxy_async_smem();  // generic-proxy writes of H -> visible to the tensor core's async reads
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(b ? hfull_leader1 : hfull_leader0);
       }
       // ---- drain O: +b2, +resid, bf16, TMA store (one 64-column sub-tile per warp group; NOSUB <= 3) ----
       const int sub = grp;
@@ -396,15 +452,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   }
 }
 
-template <int C>
+template <int C, bool TEAMS>
 int launch_ffn(const FfnFusedArgs& a, cudaStream_t stream) {
   using Cfg = FfnCfg<C>;
-  auto kfn = ffn_fused_kernel<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  auto kfn = ffn_fused_kernel<C, TEAMS>;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), Cfg::SMEM_BYTES)) return rc;
   CUtensorMap tx, tw1, tw2, to;
   if (int rc = make_tmap_bf16(&tx, a.x, a.M, C, C, FM)) return rc;
   if (int rc = make_tmap_bf16(&tw1, a.w1, a.hidden, C, C, HC / 2)) return rc;
@@ -430,8 +482,9 @@ bool ffn_fused_supported(int dtype, int C, int hidden) {
 int ffn_fused(const FfnFusedArgs& a, cudaStream_t stream) {
   FVLA_REQUIRE(a.M > 0 && ffn_fused_supported(DT_BF16, a.C, a.hidden), "ffn_fused: unsupported shape");
   FVLA_REQUIRE(a.b1 != nullptr && a.b2 != nullptr && a.resid != nullptr, "ffn_fused: biases and residual required");
-  if (a.C == 96) return launch_ffn<96>(a, stream);
-  return launch_ffn<192>(a, stream);
+  static const bool teams = std::getenv("FVLA_FFN_NO_TEAMS") == nullptr;  // A/B switch for profiling
+  if (a.C == 96) return teams ? launch_ffn<96, true>(a, stream) : launch_ffn<96, false>(a, stream);
+  return teams ? launch_ffn<192, true>(a, stream) : launch_ffn<192, false>(a, stream);
 }
 
 }  // namespace fvla

@@ -472,13 +472,8 @@ int make_tmap_f32_store(CUtensorMap* out, void* ptr, long long rows, long long c
 template <int BLOCK_N, bool SWIGLU, bool OUT_F32 = false>
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  static bool attr_set = false;
   auto kfn = gemm_bf16_tcgen05_kernel<BLOCK_N, SWIGLU, OUT_F32>;
-  if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), Cfg::SMEM_BYTES)) return rc;
   CUtensorMap ta, tw, td;
   if (int rc = make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, BLOCK_M)) return rc;
   if (int rc = make_tmap_bf16(&tw, g.W, g.N, g.K, g.ldw, Cfg::HALF_N)) return rc;

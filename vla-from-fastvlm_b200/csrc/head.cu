@@ -86,17 +86,19 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
   if (warp < R) {
     const int b = r0 + warp;
     if (b < B) {
+      // dataset normalisation of the raw state (identity unless fvla_set_io_normalization was called)
+      auto st = [&](int i) { return (states[static_cast<size_t>(b) * S + i] - w.st_mean[i]) * w.st_inv_std[i]; };
       float s = 0.f;
-      for (int i = lane; i < S; i += 32) s += states[static_cast<size_t>(b) * S + i];
+      for (int i = lane; i < S; i += 32) s += st(i);
       const float mean = warp_sum(s) / static_cast<float>(S);
       float vs = 0.f;
       for (int i = lane; i < S; i += 32) {
-        const float d = states[static_cast<size_t>(b) * S + i] - mean;
+        const float d = st(i) - mean;
         vs = fmaf(d, d, vs);
       }
       const float rstd = rsqrtf(warp_sum(vs) / static_cast<float>(S) + 1e-5f);
       for (int i = lane; i < S; i += 32)
-        sln[warp * S + i] = (states[static_cast<size_t>(b) * S + i] - mean) * rstd * w.ln_s_w[i] + w.ln_s_b[i];
+        sln[warp * S + i] = (st(i) - mean) * rstd * w.ln_s_w[i] + w.ln_s_b[i];
     } else {
       for (int i = lane; i < S; i += 32) sln[warp * S + i] = 0.f;
     }
@@ -204,7 +206,8 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
       if (lane == 0) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
-          if (r0 + r < B) actions[static_cast<size_t>(r0 + r) * A + n] = acc[0][r] + w.b_act[n];
+          if (r0 + r < B)
+            actions[static_cast<size_t>(r0 + r) * A + n] = fmaf(acc[0][r] + w.b_act[n], w.act_scale[n], w.act_shift[n]);
       }
     }
   }
@@ -217,11 +220,7 @@ int launch_head(const HeadWeights& w, const float* pooled, const float* states, 
   auto kfn = action_head_kernel<T, R>;
   const size_t smem = sizeof(float) * (static_cast<size_t>(R) * (w.H + w.Hd + 2 * w.F + w.S));
   FVLA_REQUIRE(smem <= 220 * 1024, "action head: hidden sizes too large for one CTA");
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_smem = smem;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), static_cast<int>(smem))) return rc;
   kfn<<<HEAD_CL * ceil_div(B, R), 256, smem, stream>>>(w, pooled, states, actions, state_feat, x1_scratch, fused, B);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;

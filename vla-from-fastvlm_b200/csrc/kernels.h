@@ -135,6 +135,9 @@ int attention_v2(const AttnArgs& a, cudaStream_t stream);  // reference-grade SI
 // x_f32 (bf16 mode only): x is the decoder's FP32 residual stream, out stays bf16
 int rmsnorm(int dtype, const void* x, const float* weight, void* out, int rows, int H, float eps,
             cudaStream_t stream, int x_f32 = 0);
+// LayerNorm over the channel dimension of token-major rows WITHOUT the affine part (FastViTHD `LayerNormChannel`
+// [EXT mci.py]; weight/bias are folded into the GEMM that follows): out = (x - mean) * rsqrt(var + eps), C % 8 == 0
+int layernorm_rows(int dtype, const void* x, void* out, int rows, int C, float eps, cudaStream_t stream);
 // plan[b*T+t]: >=0 vocab id, -1 zero row (padding), <=-2 image row (-2-idx) of sample b
 // out_f32 (bf16 mode only): write the rows as FP32 (the decoder's residual stream)
 int embed_splice(int dtype, const void* table, const void* img_feats, int n_img, const int* plan,
@@ -156,6 +159,10 @@ struct HeadWeights {  // all fp32 except the four matrices, which are in `dtype`
   const float* ln_f_w; const float* ln_f_b;        // fusion.1
   const void* w_f4; const float* b_f4;             // fusion.4            [F, F]
   const void* w_act; const float* b_act;           // action_head         [A, F]
+  // LeRobot (un)normaliser steps fused at both ends of the head (lerobot_fastvla/processor_fastvla.py:30-48), device
+  // fp32, never null (identity by default): state' = (state - st_mean) * st_inv_std;  action' = action * act_scale + act_shift
+  const float* st_mean; const float* st_inv_std;   // [S]
+  const float* act_scale; const float* act_shift;  // [A]
   int H, S, Hd, F, A;
 };
 // pooled [B,H] fp32, states [B,S] fp32 -> actions [B,A] fp32.  state_feat [B,Hd], x1_scratch [B,F], fused [B,F]

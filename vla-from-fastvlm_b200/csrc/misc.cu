@@ -80,6 +80,50 @@ rmsnorm_warp_kernel(const TI* __restrict__ x, const float* __restrict__ w, TO* _
   }
 }
 
+// FastViTHD LayerNormChannel without its affine part (folded into the qkv GEMM): warp per row, row kept in registers,
+// two-pass variance (mean first) in fp32.
+template <typename T, int KEEP>
+__global__ void __launch_bounds__(128)
+layernorm_rows_kernel(const T* __restrict__ x, T* __restrict__ out, int rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * C;
+  Vec8<T> keep[KEEP];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < KEEP; ++k) {
+    const int i = (k * 32 + lane) * 8;
+    if (i < C) {
+      keep[k].load(xr + i);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) s += keep[k].v[c];
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(C);
+  float vs = 0.f;
+#pragma unroll
+  for (int k = 0; k < KEEP; ++k) {
+    const int i = (k * 32 + lane) * 8;
+    if (i < C) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { const float d = keep[k].v[c] - mean; vs = fmaf(d, d, vs); }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(vs) / static_cast<float>(C) + eps);
+  T* orow = out + row * C;
+#pragma unroll
+  for (int k = 0; k < KEEP; ++k) {
+    const int i = (k * 32 + lane) * 8;
+    if (i < C) {
+      Vec8<T> o;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o.v[c] = (keep[k].v[c] - mean) * rstd;
+      o.store(orow + i);
+    }
+  }
+}
+
 template <typename TI, typename TO>
 void launch_rmsnorm(const void* x, const float* weight, void* out, int rows, int H, float eps, cudaStream_t stream) {
   const TI* xi = static_cast<const TI*>(x);
@@ -223,6 +267,23 @@ __global__ void rope_table_kernel(float* cos_t, float* sin_t, int T_len, int hal
 }
 
 }  // namespace
+
+int layernorm_rows(int dtype, const void* x, void* out, int rows, int C, float eps, cudaStream_t stream) {
+  FVLA_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 4096, "layernorm_rows: C must be a multiple of 8, <= 4096");
+  const int grid = ceil_div(rows, 4);
+  if (dtype == DT_F32) {
+    if (C <= 1024) layernorm_rows_kernel<float, 4><<<grid, 128, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(out), rows, C, eps);
+    else if (C <= 2048) layernorm_rows_kernel<float, 8><<<grid, 128, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(out), rows, C, eps);
+    else layernorm_rows_kernel<float, 16><<<grid, 128, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(out), rows, C, eps);
+  } else {
+    using B16 = __nv_bfloat16;
+    if (C <= 1024) layernorm_rows_kernel<B16, 4><<<grid, 128, 0, stream>>>(static_cast<const B16*>(x), static_cast<B16*>(out), rows, C, eps);
+    else if (C <= 2048) layernorm_rows_kernel<B16, 8><<<grid, 128, 0, stream>>>(static_cast<const B16*>(x), static_cast<B16*>(out), rows, C, eps);
+    else layernorm_rows_kernel<B16, 16><<<grid, 128, 0, stream>>>(static_cast<const B16*>(x), static_cast<B16*>(out), rows, C, eps);
+  }
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 int rmsnorm(int dtype, const void* x, const float* weight, void* out, int rows, int H, float eps,
             cudaStream_t stream, int x_f32) {

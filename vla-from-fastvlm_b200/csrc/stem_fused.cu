@@ -295,11 +295,7 @@ bool stem_fused_supported(int dtype, int S, int C) {
 int stem_fused(const void* in, const uint32_t* btab, const float* b0_half, const float* w1_packed, const float* b1,
                void* out, int B, int S, int C, cudaStream_t stream) {
   FVLA_REQUIRE(stem_fused_supported(DT_BF16, S, C), "stem_fused: unsupported geometry");
-  static bool attr_set = false;
-  if (!attr_set) {
-    FVLA_CUDA_CHECK(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SF_SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(stem_fused_kernel), SF_SMEM)) return rc;
   // the ingested image [B][S][S][4] bf16 as a 3-D tensor [B][S][4 S]: box = 36 pixels x 35 rows
   TmaEncodeTiledFn fn = tma_encode_fn();
   FVLA_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");

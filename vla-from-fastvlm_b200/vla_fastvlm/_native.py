@@ -109,6 +109,7 @@ _SIGNATURES = {
     "fvla_last_forward_flops": (C.c_double, [_VP]),
     "fvla_set_tap": (C.c_int, [_VP, _I32, _VP, _I64]),
     "fvla_merged_len": (C.c_int, [_VP]),
+    "fvla_set_io_normalization": (C.c_int, [_VP, C.POINTER(_F32), C.POINTER(_F32), C.POINTER(_F32), C.POINTER(_F32)]),
     "fvla_set_profile": (C.c_int, [_VP, _I32]),
     "fvla_profile_report": (C.c_int, [_VP, C.c_char_p, _I64]),
     "fvla_op_gemm": (C.c_int, [_I32, _VP, _I32, _VP, _I32, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP,
@@ -123,6 +124,7 @@ _SIGNATURES = {
     "fvla_op_attention": (C.c_int, [_I32, _I32, _VP, _VP, _VP, _I32, _VP, _I32, _I32, _I32, _I32, _I32,
                                     _I32, _F32, _I32, _VP, _VP, _VP]),
     "fvla_op_rmsnorm": (C.c_int, [_I32, _VP, _VP, _VP, _I32, _I32, _F32, _VP]),
+    "fvla_op_layernorm_rows": (C.c_int, [_I32, _VP, _VP, _I32, _I32, _F32, _VP]),
     "fvla_op_ffn_fused": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP]),
     "fvla_op_convert": (C.c_int, [_I32, _VP, _I32, _VP, _I64, _VP]),
 }
@@ -323,6 +325,14 @@ def op_attention(qkv: torch.Tensor, B: int, N: int, heads_q: int, heads_kv: int,
     check(load().fvla_op_attention(dtype_code(qkv.dtype), impl, q, k, v, ld, ptr(out), out.shape[1], B, N,
                                    heads_q, heads_kv, head_dim, scale, int(causal), ptr(rope_cos),
                                    ptr(rope_sin), stream_ptr()), "fvla_op_attention")
+    return out
+
+
+def op_layernorm_rows(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    out = torch.empty_like(x)
+    rows, Cc = x.shape
+    check(load().fvla_op_layernorm_rows(dtype_code(x.dtype), ptr(x), ptr(out), rows, Cc, eps, stream_ptr()),
+          "fvla_op_layernorm_rows")
     return out
 
 

@@ -15,7 +15,8 @@ _BACKBONE_FIELD_MAP = {
     "image_size": "force_image_size",
     **{k: k for k in ("freeze_backbone", "resize_with_padding", "pad_value", "tokenizer_max_length",
                       "tokenizer_padding_side", "pad_to_max_length", "compute_dtype", "image_token_mode",
-                      "pool_merged_last", "vision_chunk", "skip_unused_vision", "synthetic_seed")},
+                      "pool_merged_last", "vision_chunk", "skip_unused_vision", "synthetic_seed",
+                      "image_input_scale")},
 }
 
 

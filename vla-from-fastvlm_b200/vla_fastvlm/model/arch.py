@@ -102,6 +102,21 @@ PRESETS: Dict[str, BackboneArch] = {
                       vocab=512, max_position=2048),
         mm_vision_tower="mobileclip_l_256",
     ),
+    # Decoder-shape parity presets: the Qwen2-1.5B / 7B layer geometry (hidden, heads, head_dim 128, intermediate)
+    # at depth 2 behind the small tower at 1024^2 (256 image tokens => T' = 256 + T_text like the full models), with a
+    # small vocabulary so the CPU oracle and the host weight generation stay cheap.
+    "dec-1.5b-2l": BackboneArch(
+        name="dec-1.5b-2l",
+        vision=VisionArch(image_size=1024, layers=(1, 1, 1, 1, 1), dims=(16, 32, 64, 128, 256)),
+        text=TextArch(hidden=1536, layers=2, q_heads=12, kv_heads=2, head_dim=128, intermediate=8960, vocab=2048),
+        mm_vision_tower="mobileclip_l_1024",
+    ),
+    "dec-7b-2l": BackboneArch(
+        name="dec-7b-2l",
+        vision=VisionArch(image_size=1024, layers=(1, 1, 1, 1, 1), dims=(16, 32, 64, 128, 256)),
+        text=TextArch(hidden=3584, layers=2, q_heads=28, kv_heads=4, head_dim=128, intermediate=18944, vocab=2048),
+        mm_vision_tower="mobileclip_l_1024",
+    ),
 }
 
 
@@ -133,7 +148,13 @@ def arch_from_hf_config(cfg: Dict[str, Any]) -> BackboneArch:
         rope_theta=float(cfg.get("rope_theta", 1e6)),
         max_position=int(cfg.get("max_position_embeddings", 32768)),
     )
-    return BackboneArch(name=str(cfg.get("_name_or_path", "llava_qwen2")), vision=VisionArch(image_size=image_size),
+    vis = dict(image_size=image_size)
+    if isinstance(cfg.get("vision_arch"), dict):
+        # Not an Apple field: the checkpoints imply FastViTHD through the tower name alone.  Exports of OTHER tower
+        # geometries (the test checkpoints, distilled towers) spell the geometry out under this key.
+        for k, val in cfg["vision_arch"].items():
+            vis[k] = tuple(val) if isinstance(val, list) else val
+    return BackboneArch(name=str(cfg.get("_name_or_path", "llava_qwen2")), vision=VisionArch(**vis),
                         text=text, mm_vision_tower=tower,
                         tokenizer_padding_side=str(cfg.get("tokenizer_padding_side", "right")))
 

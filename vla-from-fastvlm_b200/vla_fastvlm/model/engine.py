@@ -60,6 +60,10 @@ class NativeEngine:
         self.arch = arch
         self.dtype = dtype
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise N.NativeError(f"the engine needs a CUDA device, got {self.device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.state_dim, self.action_dim = state_dim, action_dim
         self.hidden_dim, self.fusion_dim = hidden_dim, fusion_dim
         self.cfg = make_config(arch, dtype, state_dim, action_dim, hidden_dim, fusion_dim, pool_mode,
@@ -108,6 +112,33 @@ class NativeEngine:
         with torch.cuda.device(self.device):
             N.check(self.lib.fvla_reserve(self._h, batch, n_tokens), "fvla_reserve")
 
+    # ---- LeRobot (un)normaliser steps fused into the head kernel -------------------------------
+    def set_io_normalization(self, state_mean=None, state_std=None, action_mean=None, action_std=None,
+                             eps: float = 1e-8) -> None:
+        """state' = (state - mean) / (std + eps) in front of the head, action' = action * std + mean behind it — the
+        MEAN_STD arithmetic of LeRobot's Normalizer / Unnormalizer steps
+        (lerobot_fastvla/processor_fastvla.py:30-48).  None = identity for that part."""
+        if not self.finalized:
+            raise N.NativeError("engine not finalized")
+
+        def vec(t, n, fn):
+            if t is None:
+                return None
+            v = fn(torch.as_tensor(t, dtype=torch.float64).flatten().cpu()).to(torch.float32).contiguous()
+            if v.numel() != n:
+                raise N.NativeError(f"normalisation vector has {v.numel()} elements, expected {n}")
+            return v
+
+        keep = [vec(state_mean, self.state_dim, lambda m: m),
+                vec(state_std, self.state_dim, lambda s: 1.0 / (s + eps)),
+                vec(action_std, self.action_dim, lambda s: s),
+                vec(action_mean, self.action_dim, lambda m: m)]
+        if state_mean is None and state_std is not None:
+            raise N.NativeError("state_std without state_mean")
+        ptrs = [C.cast(v.data_ptr(), C.POINTER(C.c_float)) if v is not None else None for v in keep]
+        with torch.cuda.device(self.device):
+            N.check(self.lib.fvla_set_io_normalization(self._h, *ptrs), "fvla_set_io_normalization")
+
     # ---- taps ---------------------------------------------------------------------------------
     def set_tap(self, stage: int, buf: Optional[torch.Tensor]) -> None:
         if buf is None:
@@ -131,6 +162,9 @@ class NativeEngine:
             raise N.NativeError("engine not finalized")
         if not images.is_cuda or images.dim() != 4:
             raise N.NativeError("images must be a 4-D CUDA tensor")
+        if images.device != self.device:
+            raise N.NativeError(f"images live on {images.device} but this engine was built on {self.device}: one "
+                                "engine per device (move the policy, or the batch)")
         images = images.contiguous()
         B = images.shape[0]
         if nhwc:
@@ -177,6 +211,9 @@ class NativeEngine:
             a.pooled = pooled_out.data_ptr()
         if states is None:
             result = pooled_out
+        for name, t in (("out", out), ("pooled_out", pooled_out)):
+            if t is not None and t.device != self.device:
+                raise N.NativeError(f"{name} lives on {t.device}, engine on {self.device}")
         with torch.cuda.device(self.device):
             N.check(self.lib.fvla_forward(self._h, C.byref(a), N.stream_ptr()), "fvla_forward")
         return result

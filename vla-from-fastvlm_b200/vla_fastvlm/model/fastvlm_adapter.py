@@ -64,6 +64,7 @@ class FastVLMBackboneConfig:
     vision_chunk: int = 0              # images per FastViTHD pass (0 = engine default)
     skip_unused_vision: bool = True    # do not run the tower when no prompt holds a placeholder
     synthetic_seed: int = 0
+    image_input_scale: float = 1.0     # pixel scale applied by the ingest kernel (1/255: raw uint8 frames)
 
 
 def resize_with_pad(img: Tensor, width: int, height: int, pad_value: float = 0.0) -> Tensor:
@@ -139,9 +140,12 @@ class FastVLMBackbone(nn.Module):
         self.model.configure_engine(pool_mode=self.config.image_feature_pool,
                                     vision_chunk=self.config.vision_chunk,
                                     skip_unused_vision=self.config.skip_unused_vision)
-        if self.config.freeze_backbone:
-            for p in self.model.parameters():
-                p.requires_grad = False
+        if not self.config.freeze_backbone:
+            # The reference cannot train the backbone either: its forward is @torch.no_grad (:501).  Say so once.
+            logger.warning("freeze_backbone=False has no effect: the backbone forward runs without autograd "
+                           "(as in the reference, fastvlm_adapter.py:501); only the action head is trainable.")
+        for p in self.model.parameters():
+            p.requires_grad = False
         self._token_cache: Dict[Tuple[str, ...], Tuple[Tensor, Tensor]] = {}
         print(f"[FastVLMBackbone] expected (S,S) = ({self.expected_size},{self.expected_size})")
 
@@ -193,9 +197,18 @@ class FastVLMBackbone(nn.Module):
             from .llava_qwen2 import _read_checkpoint_tensors
 
             boot = load_arch(self.config.bootstrap_model_id.rsplit("/", 1)[-1].lower())  # "apple/FastVLM-0.5B" -> preset
+            if boot is None:
+                boot = load_arch(self.config.bootstrap_model_id)  # a local directory / "synthetic:<preset>"
             merged = dict(local_config)
             if boot is not None:
+                from dataclasses import asdict
+
                 merged.setdefault("mm_vision_tower", boot.mm_vision_tower)
+                geometry = asdict(boot.vision)
+                geometry.pop("image_size")  # follows the tower name / force_image_size, like a described checkpoint
+                merged.setdefault("vision_arch", geometry)
+            if boot is None and "mm_vision_tower" not in merged:
+                raise ValueError(f"unknown bootstrap model {self.config.bootstrap_model_id!r}")
             arch = arch_from_hf_config(merged)
             return LlavaQwen2Native(arch, _read_checkpoint_tensors(model_path), self.config.model_id,
                                     model_kwargs["compute_dtype"])
@@ -361,9 +374,12 @@ class FastVLMBackbone(nn.Module):
     def _ingest_args(self, x: Tensor) -> Dict[str, Any]:
         """Kernel arguments equivalent to `_resize_image` + `_maybe_normalize_imagenet` (:451-477)."""
         args: Dict[str, Any] = dict(letterbox=bool(self.config.resize_with_padding),
-                                    pad_value=float(self.config.pad_value), img_scale=1.0, mean=None, std=None)
+                                    pad_value=float(self.config.pad_value),
+                                    img_scale=float(self.config.image_input_scale), mean=None, std=None)
         if self.config.normalize_imagenet:
-            if float(x.max()) > 1.5:  # 0..255 input (reference :472-473)
+            # 0..255 input (reference :472-473).  uint8 frames answer this from the dtype; a float batch needs its
+            # maximum, i.e. one device->host sync per call — only on this opt-in path.
+            if self.config.image_input_scale == 1.0 and (x.dtype == torch.uint8 or float(x.max()) > 1.5):
                 args["img_scale"] = 1.0 / 255.0
             args["mean"], args["std"] = _IMAGENET_MEAN, _IMAGENET_STD
         return args
@@ -409,11 +425,19 @@ class FastVLMBackbone(nn.Module):
         return self._run(images, tasks, None, device)
 
     def _run(self, images, tasks: List[str], states: Optional[Tensor], device: torch.device | None) -> Tensor:
-        if device is None:
-            device = next(self.model.parameters()).device
-        device = torch.device(device)
-        if device.type != "cuda":
-            raise N.NativeError("the FastVLA B200 path runs on CUDA only (no CPU fallback)")
+        # The engine lives where the module lives (`policy.to("cuda:1")` moves it); `device` is accepted for API
+        # compatibility (reference :501-513 moves its inputs there) but cannot disagree with the module.
+        home = self.model.device
+        if home.type != "cuda":
+            raise N.NativeError("the FastVLA B200 path runs on CUDA only (no CPU fallback): move the policy to a "
+                                "CUDA device")
+        if device is not None:
+            device = torch.device(device)
+            if device.type != "cuda":
+                raise N.NativeError("the FastVLA B200 path runs on CUDA only (no CPU fallback)")
+            if device.index is not None and home.index is not None and device.index != home.index:
+                raise ValueError(f"device={device} but the backbone lives on {home}; move the policy with .to(device)")
+        device = home
         x, nhwc = self._as_batch(images)
         x = self._device_image(x, device)
         if len(tasks) != x.shape[0]:

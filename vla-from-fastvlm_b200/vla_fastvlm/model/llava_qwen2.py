@@ -7,6 +7,12 @@ trust_remote_code=True)` (src/vla_fastvlm/model/fastvlm_adapter.py:183-201) and 
 until the CUDA engine is built, exposes the `config` attributes the adapter inspects
 (`hidden_size`, `mm_vision_tower`, `model_type`), and forwards to libfvla.  There is no PyTorch
 implementation of the network here — without the CUDA library nothing runs.
+
+Checkpoint contract (reference `policy_state_dict.pt`, training/trainer.py:246-255 -> utils/checkpoint.py:14-47):
+the HF module's tensors appear in the policy's `state_dict()` under `model.backbone.model.<hf name>` and
+`load_state_dict(strict=True)` consumes them.  The module therefore keeps the checkpoint tensors (host memory, stored
+dtype) next to the engine's packed device copies, serialises them under their HF names, and rebuilds the engine when a
+`load_state_dict` replaces them.
 """
 from __future__ import annotations
 
@@ -54,7 +60,8 @@ class LlavaQwen2Native(nn.Module):
         super().__init__()
         self.arch = arch
         self.compute_dtype = compute_dtype
-        self._pending_sd: Optional[Dict[str, torch.Tensor]] = state_dict
+        # checkpoint tensors under their HF names (host memory): source of the engine build AND of state_dict()
+        self._weights: Dict[str, torch.Tensor] = {k: v.detach() for k, v in state_dict.items()}
         self._engine: Optional[NativeEngine] = None
         self._head_spec: Optional[Tuple[int, int, int, int]] = None
         self._head_sd_fn: Optional[Callable[[], Dict[str, torch.Tensor]]] = None
@@ -70,9 +77,51 @@ class LlavaQwen2Native(nn.Module):
             output_hidden_states=False,
             _name_or_path=name_or_path,
         )
-        # lets callers do `next(model.parameters()).device` like on the HF module (adapter :510)
+        # follows .to(device) / .cuda() like a parameter would, but never shows up in state_dict()
         dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-        self._device_anchor = nn.Parameter(torch.zeros(1, device=dev), requires_grad=False)
+        self.register_buffer("_device_anchor", torch.zeros(1, device=dev), persistent=False)
+
+    @property
+    def device(self) -> torch.device:
+        return self._device_anchor.device
+
+    # ---- state dict: the HF tensors under their HF names -----------------------------------------
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        for k, v in self._weights.items():
+            destination[prefix + k] = v
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        touched = False
+        for k, cur in self._weights.items():
+            key = prefix + k
+            if key not in state_dict:
+                if not k.startswith("lm_head."):  # never computed: kept for round trips, never required
+                    missing_keys.append(key)
+                continue
+            new = state_dict[key]
+            if tuple(new.shape) != tuple(cur.shape):
+                error_msgs.append(f"size mismatch for {key}: copying a param with shape {tuple(new.shape)} from "
+                                  f"checkpoint, the shape in current model is {tuple(cur.shape)}.")
+                continue
+            self._weights[k] = new.detach().to("cpu")
+            touched = True
+        for key in state_dict:
+            if key.startswith(prefix):
+                k = key[len(prefix):]
+                # the LM head is never computed; tied checkpoints list it next to embed_tokens
+                if k not in self._weights and not k.startswith("lm_head."):
+                    unexpected_keys.append(key)
+        if touched:
+            self._engine = None  # packed device copies are stale: rebuilt from the new tensors on the next forward
+
+    def _apply(self, fn, recurse=True):
+        before = self._device_anchor.device
+        out = super()._apply(fn, recurse)
+        if self._engine is not None and self._device_anchor.device != before:
+            self._engine = None  # the engine lives on ONE device: rebuild where the module now is
+        return out
 
     # ---- construction ---------------------------------------------------------------------------
     @classmethod
@@ -102,6 +151,15 @@ class LlavaQwen2Native(nn.Module):
                 f"The checkpoint you are trying to load has model type `{hf_cfg.get('model_type')}` but the native "
                 "FastVLA engine does not recognize this architecture (only `llava_qwen2`)."
             )
+        if "mm_vision_tower" not in hf_cfg and "vision" not in hf_cfg:
+            # Same situation as the reference's stock path on a local export without `auto_map`
+            # (fastvlm_adapter.py:183-206): the config names the architecture but does not describe it; the defaults
+            # live with the bootstrap model.  Same message shape, so `_needs_llava_qwen2_bootstrap` routes it.
+            raise ValueError(
+                "The checkpoint you are trying to load has model type `llava_qwen2` but its config.json does not "
+                "describe the vision tower (no `mm_vision_tower`): the loader does not recognize this architecture "
+                "without the bootstrap model's defaults."
+            )
         arch = arch_from_hf_config(hf_cfg)
         return cls(arch, _read_checkpoint_tensors(path), model_id, compute_dtype)
 
@@ -125,12 +183,15 @@ class LlavaQwen2Native(nn.Module):
         return self._engine
 
     def _build_engine(self) -> None:
-        if self._pending_sd is None:
-            raise RuntimeError("backbone weights were already released")
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("the FastVLA B200 path runs on CUDA only: move the policy to a CUDA device first "
+                               "(no CPU fallback)")
         spec = self._head_spec or (0, 0, 0, 0)
         eng = NativeEngine(self.arch, dtype=self.compute_dtype, state_dim=spec[0], action_dim=spec[1],
-                           hidden_dim=spec[2], fusion_dim=spec[3], **self._engine_opts)
-        eng.load_state_dict(self._pending_sd, prefix=BACKBONE_KEY_PREFIX)
+                           hidden_dim=spec[2], fusion_dim=spec[3], device=dev, **self._engine_opts)
+        eng.load_state_dict({k: v for k, v in self._weights.items() if not k.startswith("lm_head.")},
+                            prefix=BACKBONE_KEY_PREFIX)
         if self._head_sd_fn is not None:
             eng.load_state_dict(self._head_sd_fn())
         missing = eng.missing_tensors()
@@ -138,7 +199,6 @@ class LlavaQwen2Native(nn.Module):
             raise RuntimeError(f"checkpoint is missing {len(missing)} tensors, e.g. {missing[:3]}")
         eng.finalize()
         self._engine = eng
-        self._pending_sd = None  # packed copies live on the device now
 
     def refresh_head(self) -> None:
         """Push the current (possibly just-trained) head parameters into the engine."""

@@ -47,7 +47,12 @@ class _Init:
         sd[prefix + ".running_var"] = self.uniform(c, lo=0.6, hi=1.4)
 
 
-def synthetic_backbone_state_dict(arch: "BackboneArch", seed: int = 0) -> Dict[str, torch.Tensor]:
+def synthetic_backbone_state_dict(arch: "BackboneArch", seed: int = 0,
+                                  attn_norm: str = "batchnorm") -> Dict[str, torch.Tensor]:
+    """`attn_norm`: the layer in front of MHSA — "batchnorm" (BatchNorm2d: weight, bias, running stats) or "layernorm"
+    (LayerNormChannel: weight and bias only); the engine and the oracle tell them apart by the key set."""
+    if attn_norm not in ("batchnorm", "layernorm"):
+        raise ValueError("attn_norm must be 'batchnorm' or 'layernorm'")
     r = _Init(seed)
     sd: Dict[str, torch.Tensor] = {}
     v, t = arch.vision, arch.text
@@ -83,6 +88,8 @@ def synthetic_backbone_state_dict(arch: "BackboneArch", seed: int = 0) -> Dict[s
             base = P + f"network.{idx}.{j}"
             if v.attention[i]:
                 r.bn(sd, base + ".norm", d)
+                if attn_norm == "layernorm":
+                    del sd[base + ".norm.running_mean"], sd[base + ".norm.running_var"]
                 # q/k gains chosen so softmax logits have std ~2 (not one-hot, not uniform) on O(0.2) inputs
                 sd[base + ".token_mixer.qkv.weight"] = torch.cat(
                     [r.linear(d, d, 7.0), r.linear(d, d, 7.0), r.linear(d, d, 3.0)], dim=0)

@@ -48,6 +48,10 @@ class FastVLAModelFields:
     vision_chunk: int = 0
     skip_unused_vision: bool = True
     synthetic_seed: int = 0
+    image_input_scale: float = 1.0      # multiplies raw pixel values inside the ingest kernel: 1/255 takes uint8 camera
+                                        # frames (HWC or CHW) straight from the host, 4x fewer PCIe bytes than fp32 [0,1]
+    fuse_io_normalization: bool = False  # LeRobot plugin: the STATE normaliser and the ACTION unnormaliser of the
+                                         # pre/post pipelines run inside the action-head kernel instead
 
 
 MODEL_FIELD_NAMES = tuple(f.name for f in fields(FastVLAModelFields))
