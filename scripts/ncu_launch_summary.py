@@ -56,7 +56,21 @@ def main() -> None:
         for name, k in per.items():
             if "tcgen05" in name or "ffn_fused" in name:
                 fam["launches"] += k["n"]; fam["dram_bytes"] += k["rd"] + k["wr"]; fam["ms"] += k["ns"] / 1e6
-        json.dump({"source": src, "tcgen05_gemm_family": fam, "total_ms": tot / 1e6}, open(out_json, "w"), indent=1)
+        # per kernel (template instances merged): what bench.py reports as roofline_kernels[*].traffic
+        kernels = {}
+        alias = {"gemm_bf16_tcgen05_kernel": "gemm_bf16_tcgen05_kernel", "ffn_fused_kernel": "ffn_fused_kernel",
+                 "dwconv7_mma_kernel": "dwconv7_mma_kernel", "dwconv3_tma_kernel": "dwconv3_tma_kernel",
+                 "dwconv7_s2m2": "dwconv7_s2m2_kernel", "stem_fused_kernel": "stem_fused_kernel",
+                 "attn_tc_kernel": "attention_vis", "flash_attn_v2_kernel": "attention_vis",
+                 "flash_attn_gqa_kernel": "attention_llm"}
+        for name, k in per.items():
+            for pat, key in alias.items():
+                if pat in name:
+                    d = kernels.setdefault(key, dict(launches=0, dram_bytes=0.0, ms=0.0))
+                    d["launches"] += k["n"]; d["dram_bytes"] += k["rd"] + k["wr"]; d["ms"] += k["ns"] / 1e6
+                    break
+        json.dump({"source": src, "tcgen05_gemm_family": fam, "kernels": kernels, "total_ms": tot / 1e6},
+                  open(out_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
