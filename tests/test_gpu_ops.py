@@ -361,6 +361,9 @@ ATTN_CASES = [
     (3, 33, 28, 4, 128, True, False),      # grouped-query kernel: Qwen2-7B grouping (7 heads per kv head), ragged N
     (2, 290, 8, 1, 64, True, False),       # grouped-query kernel: largest group (8 warps), 5 kv tiles
     (2, 64, 6, 3, 64, True, False),        # grouped-query kernel: group of 2, N a multiple of the tile
+    (2, 1024, 24, 24, 32, False, False),   # FastViTHD stage-3 MHSA: tcgen05 / tensor-memory kernel (attention_sm100.cu)
+    (3, 256, 48, 48, 32, False, False),    # FastViTHD stage-4 MHSA: same kernel, 4 key tiles
+    (1, 384, 6, 2, 32, False, False),      # same kernel, grouped kv heads, odd tile count
 ]
 
 

@@ -348,6 +348,7 @@ int attention(int dtype, const AttnArgs& a, cudaStream_t stream) {
   if (int rc = check_attn(a)) return rc;
   if (dtype == DT_F32) return launch_simt<float>(a, stream);
   // short causal prefills (T' = 272: three 128-row blocks, the last one nearly empty) keep the 64-query kernel
+  if (attention_tc_supported(a)) return attention_tc(a, stream);  // FastViTHD MHSA shapes: tensor-memory flash kernel
   if (attention_v2_supported(a)) return attention_v2(a, stream);
   const bool rope = a.rope_cos != nullptr;
   if (a.head_dim == 32 && !a.causal && !rope) return launch_flash<32, false, false>(a, stream);

@@ -127,6 +127,9 @@ struct AttnArgs {
 };
 int attention(int dtype, const AttnArgs& a, cudaStream_t stream);       // bf16: mma.sync flash; f32: SIMT
 int attention_simt(int dtype, const AttnArgs& a, cudaStream_t stream);
+// bf16, head_dim 32, non-causal, N % 128 == 0 (FastViTHD MHSA): tcgen05 MMAs with S/P/O in tensor memory (attention_sm100.cu)
+bool attention_tc_supported(const AttnArgs& a);
+int attention_tc(const AttnArgs& a, cudaStream_t stream);
 // bf16, no rotary: 128-query CTAs, cp.async double buffering, ldmatrix operands (attention_v2.cu)
 bool attention_v2_supported(const AttnArgs& a);
 int attention_v2(const AttnArgs& a, cudaStream_t stream);  // reference-grade SIMT for either dtype

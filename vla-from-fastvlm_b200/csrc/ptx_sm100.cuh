@@ -154,6 +154,58 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// one fp32 column for the warp's 32 lanes
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+// registers -> TMEM: thread i of the warp writes lane (base+i), N consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M x 16 bf16, lane = row, one 32-bit column per K pair) comes from
+// tensor memory — the softmax probabilities of the attention kernel never touch shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 // ---------------- CTA pairs (cta_group::2): cluster addressing, remote barrier ops, paired tcgen05 ----------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -230,6 +282,26 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1u) << 46;                    // descriptor version
   d |= static_cast<uint64_t>(2u) << 61;                    // SWIZZLE_128B
   return d;
+}
+// Operand tiles with 64-byte rows (32 bf16) under the 64-byte swizzle, as a TMA box {32 elements, rows} with
+// CU_TENSOR_MAP_SWIZZLE_64B lands them: 8-row groups are 512 B apart (SBO).  The same bytes serve as a K-major
+// operand (rows = M/N index, the 32 elements = K: two 16-wide MMA steps, +32 B each) and as an MN-major operand
+// (rows = K index, the 32 elements = N; canonical form Swizzle<2,4,3> o ((4,1),(8,k)):((1,LBO),(4,SBO)) in 16-byte
+// units, CUTLASS cute/atom/mma_traits_sm100.hpp) — which of the two is selected by the instruction descriptor's
+// major bits, not by the shared-memory descriptor.
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);  // start address
+  d |= static_cast<uint64_t>(1u) << 16;                    // leading byte offset (single atom wide: unused)
+  d |= static_cast<uint64_t>(512u >> 4) << 32;             // stride byte offset: next 8-row group
+  d |= static_cast<uint64_t>(1u) << 46;                    // descriptor version
+  d |= static_cast<uint64_t>(4u) << 61;                    // SWIZZLE_64B
+  return d;
+}
+// bf16 x bf16 -> fp32 with the B operand MN-major (its N index is the contiguous one in shared memory)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
 }
 // fp16 x fp16 -> fp32 (A/B format fields 0), both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
