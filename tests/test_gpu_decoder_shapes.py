@@ -27,7 +27,7 @@ def test_wide_decoder_matches_oracle(preset, dtype):
     sd = synthetic_backbone_state_dict(arch, 0)
     hsd = synthetic_head_state_dict(t.hidden, HEAD["state_dim"], HEAD["action_dim"], HEAD["hidden_dim"],
                                     HEAD["fusion_dim"], 1)
-    B, T = 3, 17
+    B, T = 4, 17   # M = 4 * 272 = 1088 rows: the fused-norm ("emit") decoder path; B = 1 runs the split-K path below
     images, states, ids, mask = make_inputs(B, 240, 320, T, t.vocab, HEAD["state_dim"], seed=21, image_mode="prefix")
     taps = {}
     ref = FastVLAOracle(arch, sd, hsd).forward(images, states, ids, mask, taps=taps)
@@ -65,3 +65,9 @@ def test_wide_decoder_matches_oracle(preset, dtype):
         assert err <= 1e-3, (err, errs)
     else:
         assert rel <= 2e-2, (rel, errs)
+    # a single observation (M = T' rows): split-K stream updates + weight-less norm kernel; same actions as in the batch
+    one = eng.forward(images[:1].to(dev), ids[:1], mask[:1].sum(1), states=states[:1].to(dev)).float().cpu()
+    if dtype == torch.float32:
+        assert (one[0] - ref[0]).abs().max() <= 1e-3
+    else:
+        assert float((one[0] - ref[0]).abs().max() / ref.abs().max()) <= 2e-2

@@ -698,7 +698,7 @@ int Engine::tap(int stage, const void* src, size_t bytes, size_t off, cudaStream
 // Forward
 // ---------------------------------------------------------------------------------------------
 int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, const void* resid,
-                     bool swiglu, cudaStream_t s, bool ab_f16, bool out_f32) {
+                     bool swiglu, cudaStream_t s, bool ab_f16, bool out_f32, bool rope, int split_k) {
   GemmArgs g;
   g.A = A; g.lda = w.K;
   g.W = w.w; g.ldw = w.K;
@@ -710,6 +710,13 @@ int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, con
   g.swiglu = swiglu ? 1 : 0;
   g.ab_f16 = ab_f16 ? 1 : 0;
   g.out_f32 = (out_f32 && cfg.dtype == FVLA_BF16) ? 1 : 0;  // the fp32 mode's D is FP32 anyway
+  if (cfg.dtype == FVLA_BF16) {
+    if (rope) {
+      g.rope_tab = rope_tab_; g.rope_T = merged_T_;
+      g.rope_cols = (cfg.n_q_heads + cfg.n_kv_heads) * cfg.head_dim;
+    }
+    if (g.out_f32 && resid == D) g.split_k = split_k;
+  }
   ++launches;
   const double fl = 2.0 * M * static_cast<double>(w.N) * w.K;
   flops += fl;
@@ -721,6 +728,7 @@ int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, con
                            static_cast<double>(M) * g.ldd + (resid ? static_cast<double>(M) * w.N : 0.0));
     prof_end(std::string(prof_scope_) + "gemm M" + std::to_string(M) + " N" + std::to_string(w.N) + " K" +
                  std::to_string(w.K) + (swiglu ? " swiglu" : "") + (resid ? " +res" : "") +
+                 (g.rope_tab ? " rope" : "") + (g.split_k > 1 ? " splitk" + std::to_string(g.split_k) : "") +
                  ((act == ACT_GELU || act == ACT_GELU_HALF_F16) ? " gelu" : ""),
              fl, by, s);
   }
@@ -841,6 +849,17 @@ int Engine::reserve(int B, int n_tokens) {
     if (int rc = ensure("rope_sin", sn.size() * 4, &ps)) return rc;
     FVLA_CUDA_CHECK(cudaMemcpy(pc, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
     FVLA_CUDA_CHECK(cudaMemcpy(ps, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
+    {
+      std::vector<uint32_t> tab(c.size());
+      for (size_t i = 0; i < c.size(); ++i) {
+        const __half2 h = __floats2half2_rn(c[i], sn[i]);
+        std::memcpy(&tab[i], &h, 4);
+      }
+      void* pt;
+      if (int rc = ensure("rope_tab", tab.size() * 4, &pt)) return rc;
+      FVLA_CUDA_CHECK(cudaMemcpy(pt, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+      rope_tab_ = static_cast<uint32_t*>(pt);
+    }
     rope_cos_ = static_cast<float*>(pc);
     rope_sin_ = static_cast<float*>(ps);
     rope_len_ = static_cast<int>(Tm);
@@ -1114,36 +1133,61 @@ int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image
   prof_end("llm.embed_splice", 0.0, M * static_cast<double>(H) * (e + 4), s);
   if (int rc = tap_stream(FVLA_TAP_EMBEDS)) return rc;
   const int nq = cfg.n_q_heads, nkv = cfg.n_kv_heads, hd = cfg.head_dim;
+  merged_T_ = Tm;
+  // bf16-mode layer fusions:
+  //  * RoPE runs in the epilogue of the qkv projection (head_dim 64: a 64-column epilogue sub-tile is one head)
+  //  * small batches (the b = 1 select_action prefill, M = T' rows): the 28 output tiles of the o-proj / down-proj
+  //    cannot fill 74 CTA pairs while each walks the whole K loop, so those GEMMs split K over several pairs — their
+  //    epilogue already reduce-adds into the fp32 stream, which makes the partial sums order-free
+  // RMSNorm stays a kernel of its own: folding it into the projections (norm weight into W's columns, rstd as a row
+  // scale of the accumulator) needs the producer's epilogue to emit the bf16 operand rows and their sums of squares,
+  // i.e. to READ the fp32 stream it now only reduce-adds into.  Built and measured at batch 64: o-proj 1.13 -> 3.32,
+  // down-proj 3.18 -> 4.24 ms/step against 0.98 ms/step for the 48 norm launches it removed (profiles/): the epilogue
+  // then moves 2.5x the bytes of the K = 896 GEMM's operands.  The norm kernel runs at 4.6 TB/s.
+  static const bool fuse_on = std::getenv("FVLA_DISABLE_LAYER_FUSION") == nullptr;  // A/B switch for profiling
+  const bool rope_fused = fuse_on && cfg.dtype == FVLA_BF16 && hd == 64 && Tm >= 32 && rope_tab_ != nullptr;
+  int split_o = 0, split_down = 0;
+  if (fuse_on && cfg.dtype == FVLA_BF16) {
+    const int pairs = num_sms() / 2;
+    const int tiles = ceil_div(M, 256) * ceil_div(H, 64);   // small-M GEMMs run 64-wide tiles
+    const int want = pairs / std::max(1, tiles);
+    if (want >= 2) {
+      split_o = std::min(want, std::max(1, (nq * hd) / 256));          // >= 4 k-blocks per split
+      split_down = std::min(std::min(want, 8), std::max(1, cfg.intermediate / 256));
+    }
+  }
   for (int l = 0; l < cfg.n_layers; ++l) {
     DecLayer& L = layers_[l];
     ++launches;
     prof_begin(s);
     if (int rc = rmsnorm(cfg.dtype, X, L.ln1, Xn, M, H, cfg.rms_eps, s, stream32)) return rc;
     prof_end("llm.rmsnorm", 0.0, M * static_cast<double>(H) * (e + 4), s);
-    if (int rc = run_gemm(L.qkv, Xn, QKV, M, ACT_NONE, nullptr, false, s)) return rc;
+    if (int rc = run_gemm(L.qkv, Xn, QKV, M, ACT_NONE, nullptr, false, s, false, false, rope_fused)) return rc;
     AttnArgs at;
     at.q = QKV; at.k = QKV + static_cast<size_t>(nq * hd) * e; at.v = QKV + static_cast<size_t>((nq + nkv) * hd) * e;
     at.ld_qkv = (nq + 2 * nkv) * hd; at.o = AO; at.ld_o = nq * hd;
     at.B = B; at.N = Tm; at.heads_q = nq; at.heads_kv = nkv; at.head_dim = hd;
     at.scale = 1.0f / std::sqrt(static_cast<float>(hd));
-    at.causal = 1;  // q and k were rotated in place just above
-    ++launches;
-    prof_begin(s);
-    if (int rc = rope_inplace(cfg.dtype, QKV, at.ld_qkv, B, Tm, nq + nkv, hd, rope_cos_, rope_sin_, s)) return rc;
-    prof_end("llm.rope", 0.0, 2.0 * M * static_cast<double>((nq + nkv) * hd) * e, s);
+    at.causal = 1;  // q and k arrive rotated (qkv epilogue, or in place just below)
+    if (!rope_fused) {
+      ++launches;
+      prof_begin(s);
+      if (int rc = rope_inplace(cfg.dtype, QKV, at.ld_qkv, B, Tm, nq + nkv, hd, rope_cos_, rope_sin_, s)) return rc;
+      prof_end("llm.rope", 0.0, 2.0 * M * static_cast<double>((nq + nkv) * hd) * e, s);
+    }
     ++launches;
     flops += 2.0 * B * static_cast<double>(Tm) * Tm * nq * hd;  // causal: half of 4*T^2*d
     prof_begin(s);
     if (int rc = attention(cfg.dtype, at, s)) return rc;
     prof_end("llm.attention T" + std::to_string(Tm), 2.0 * B * static_cast<double>(Tm) * Tm * nq * hd,
              static_cast<double>(M) * e * ((nq + 2 * nkv) * hd + nq * hd), s);
-    if (int rc = run_gemm(L.o, AO, X, M, ACT_NONE, X, false, s, false, true)) return rc;
+    if (int rc = run_gemm(L.o, AO, X, M, ACT_NONE, X, false, s, false, true, false, split_o)) return rc;
     ++launches;
     prof_begin(s);
     if (int rc = rmsnorm(cfg.dtype, X, L.ln2, Xn, M, H, cfg.rms_eps, s, stream32)) return rc;
     prof_end("llm.rmsnorm", 0.0, M * static_cast<double>(H) * (e + 4), s);
     if (int rc = run_gemm(L.gate_up, Xn, ACTB, M, ACT_NONE, nullptr, true, s)) return rc;
-    if (int rc = run_gemm(L.down, ACTB, X, M, ACT_NONE, X, false, s, false, true)) return rc;
+    if (int rc = run_gemm(L.down, ACTB, X, M, ACT_NONE, X, false, s, false, true, false, split_down)) return rc;
     if (int rc = tap_stream(FVLA_TAP_LAYER0 + l)) return rc;
   }
   // ---- final norm + pooling ----

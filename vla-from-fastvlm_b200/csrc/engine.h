@@ -98,8 +98,9 @@ class Engine {
   int ensure(const std::string& name, size_t bytes, void** out);
   int tap(int stage, const void* src, size_t bytes, size_t dst_offset_bytes, cudaStream_t s);
 
+  // rope: rotate the q and k heads in the epilogue (qkv projection, head_dim 64); split_k: see GemmArgs
   int run_gemm(const GemmW& w, const void* A, void* D, int M, int act, const void* resid, bool swiglu,
-               cudaStream_t s, bool ab_f16 = false, bool out_f32 = false);
+               cudaStream_t s, bool ab_f16 = false, bool out_f32 = false, bool rope = false, int split_k = 0);
   int run_ffn(const VisBlock& blk, const void* z, void* hid, void* out_resid, int M, cudaStream_t s);
   int run_dw(const DwW& w, const void* in, void* out, int B, int H, int W, cudaStream_t s);
   int vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats, cudaStream_t s);
@@ -132,6 +133,8 @@ class Engine {
   std::vector<DecLayer> layers_;
   float* final_norm_ = nullptr;
   float* rope_cos_ = nullptr; float* rope_sin_ = nullptr; int rope_len_ = 0;
+  uint32_t* rope_tab_ = nullptr;   // the same table as (cos, sin) fp16 pairs [pos][head_dim/2]: RoPE epilogue of the qkv GEMM
+  int merged_T_ = 1;               // T' of the forward being launched (row -> position)
   HeadWeights head_{};
   float* io_norm_ = nullptr;  // [S mean | S inv_std | A scale | A shift]
 

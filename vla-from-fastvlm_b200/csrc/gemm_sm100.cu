@@ -16,6 +16,8 @@
 //
 //
 // Edges need no special code: TMA zero-fills out-of-bounds loads (M, N and K tails) and clips stores.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "kernels.h"
@@ -59,11 +61,14 @@ struct EpiParams {
   int act;
   int ab_f16;                  // operands are fp16 (instruction descriptor formats), else bf16
   int out_f32;                 // D and resid are FP32 (the decoder's residual stream): two 32-column TMA stores per sub-tile
+  const uint32_t* rope_tab;    // [rope_T][32] (cos, sin) fp16 pairs or null: RoPE on output columns < rope_cols
+  int rope_T, rope_cols;
+  int split_k;                 // >= 1
 };
 
 using namespace epi;
 
-template <int BLOCK_N, bool SWIGLU, bool OUT_F32>
+template <int BLOCK_N, bool SWIGLU, bool OUT_F32, bool ROPE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_w,
@@ -98,8 +103,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int num_m = (p.M + PAIR_M - 1) / PAIR_M;
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = num_m * num_n;
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb_all = (p.K + BLOCK_K - 1) / BLOCK_K;
+  // split-K: a work item is (tile, split); split s covers k-blocks [s * kb_per, min((s + 1) * kb_per, num_kb_all))
+  const int kb_per = (num_kb_all + p.split_k - 1) / p.split_k;
+  const int num_tiles = num_m * num_n * p.split_k;
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -132,10 +139,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      for (int work = pair_id; work < num_tiles; work += num_pairs) {
+        const int tile = work / p.split_k, ks = work - tile * p.split_k;
         const int m0 = (tile / num_n) * PAIR_M + static_cast<int>(cta_rank) * BLOCK_M;
         const int n0 = (tile % num_n) * BLOCK_N + static_cast<int>(cta_rank) * Cfg::HALF_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_end = min(num_kb_all, (ks + 1) * kb_per);
+        for (int kb = ks * kb_per; kb < kb_end; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t full_leader = ptx::mapa_rank(full_bar(stage), 0);
           ptx::mbar_arrive_expect_tx_cluster(full_leader, Cfg::STAGE_BYTES);
@@ -155,7 +164,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      for (int work = pair_id; work < num_tiles; work += num_pairs) {
+        const int ks = work % p.split_k;
+        const int num_kb = min(num_kb_all, (ks + 1) * kb_per) - ks * kb_per;
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -199,7 +210,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int n_out_total = SWIGLU ? p.N / 2 : p.N;
     const uint32_t tempty_leader0 = ptx::mapa_rank(tempty_bar(0), 0);
     const uint32_t tempty_leader1 = ptx::mapa_rank(tempty_bar(1), 0);
-    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+    for (int work = pair_id; work < num_tiles; work += num_pairs) {
+      const int tile = work / p.split_k;
+      const bool first_split = work - tile * p.split_k == 0;  // the bias is added by exactly one split
       const int m0 = (tile / num_n) * PAIR_M + static_cast<int>(cta_rank) * BLOCK_M;
       const int n0 = (tile % num_n) * BLOCK_N;
       const int m = m0 + row;
@@ -217,6 +230,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // the TMA store this warp issued from its slab last time must have finished reading it
         if (lane == 0) ptx::tma_store_wait_read<0>();
         __syncwarp();
+        if (ROPE && out_col0 < p.rope_cols) {
+          // RoPE head: the (cos, sin) rows of this warp's 32 positions (32 x 128 B of fp16 pairs) go through the slab,
+          // loaded coalesced under the wait for the MMAs; each thread reads its own row back below
+          const int base_pos = (m0 + ew * 32) % p.rope_T;
+          uint4 tt[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = i * 32 + lane;
+            const int rrow = idx >> 3, rchunk = idx & 7;
+            int pos = base_pos + rrow;
+            if (pos >= p.rope_T) pos -= p.rope_T;
+            tt[i] = __ldg(reinterpret_cast<const uint4*>(p.rope_tab + static_cast<size_t>(pos) * 32) + rchunk);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = i * 32 + lane;
+            const int rrow = idx >> 3, rchunk = idx & 7;
+            const uint32_t dst = slab + rrow * 128 + ((rchunk ^ (rrow & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(tt[i].x), "r"(tt[i].y),
+                         "r"(tt[i].z), "r"(tt[i].w)
+                         : "memory");
+          }
+          __syncwarp();
+        }
         if (!SWIGLU && !OUT_F32 && p.resid != nullptr) {
           // residual sub-tile (32 rows x 128 B): coalesced 16-byte loads into the slab
           uint4 rr[8];
@@ -247,6 +284,86 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t tmem_acc =
           tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 
+      if constexpr (ROPE) {
+        if (has_sub && out_col0 < p.rope_cols) {
+          // ---- qkv projection epilogue with RoPE (Qwen2 apply_rotary_pos_emb, rotate_half): this sub-tile is one
+          // head of 64 columns and column j pairs with j + 32, so the halves leave TMEM 16 columns at a time ----
+          uint4 hold0 = make_uint4(0u, 0u, 0u, 0u), hold1 = hold0;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint32_t ra[16], rb[16];
+            ptx::tmem_ld_32x16(tmem_acc + static_cast<uint32_t>(acc_col0 + 16 * q), ra);
+            ptx::tmem_ld_32x16(tmem_acc + static_cast<uint32_t>(acc_col0 + 32 + 16 * q), rb);
+            uint32_t cs[16];  // this row's (cos, sin) pairs for rotation indices 16q .. 16q+15
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(cs[4 * c]), "=r"(cs[4 * c + 1]), "=r"(cs[4 * c + 2]), "=r"(cs[4 * c + 3])
+                           : "r"(sbase + (((4 * q + c) ^ (lane & 7)) << 4)));
+            const int nb = n0 + acc_col0 + 16 * q;
+            float4 ba[4], bb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ba[j] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              bb[j] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + 32) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            ptx::tmem_ld_wait();
+            float lo[16], hi[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a4[4] = {ba[j].x, ba[j].y, ba[j].z, ba[j].w}, b4[4] = {bb[j].x, bb[j].y, bb[j].z, bb[j].w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const __half2 h2 = *reinterpret_cast<const __half2*>(&cs[4 * j + t]);
+                const float c = __low2float(h2), sn = __high2float(h2);
+                const float x1 = __uint_as_float(ra[4 * j + t]) + a4[t];
+                const float x2 = __uint_as_float(rb[4 * j + t]) + b4[t];
+                lo[4 * j + t] = x1 * c - x2 * sn;
+                hi[4 * j + t] = fmaf(x2, c, x1 * sn);
+              }
+            }
+            // Outputs overwrite this thread's own table row: q == 0 consumed table chunks 0-3 and produces output
+            // chunks 0,1 (low half) and 4,5 (high half) — 4,5 still hold table pairs for q == 1, so they wait in registers
+            if (q == 0) {
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (((c) ^ (lane & 7)) << 4)),
+                             "r"(pack_bf16(lo[8 * c], lo[8 * c + 1])), "r"(pack_bf16(lo[8 * c + 2], lo[8 * c + 3])),
+                             "r"(pack_bf16(lo[8 * c + 4], lo[8 * c + 5])), "r"(pack_bf16(lo[8 * c + 6], lo[8 * c + 7]))
+                             : "memory");
+              hold0 = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+              hold1 = make_uint4(pack_bf16(hi[8], hi[9]), pack_bf16(hi[10], hi[11]), pack_bf16(hi[12], hi[13]), pack_bf16(hi[14], hi[15]));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (((2 + c) ^ (lane & 7)) << 4)),
+                             "r"(pack_bf16(lo[8 * c], lo[8 * c + 1])), "r"(pack_bf16(lo[8 * c + 2], lo[8 * c + 3])),
+                             "r"(pack_bf16(lo[8 * c + 4], lo[8 * c + 5])), "r"(pack_bf16(lo[8 * c + 6], lo[8 * c + 7]))
+                             : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (((6 + c) ^ (lane & 7)) << 4)),
+                             "r"(pack_bf16(hi[8 * c], hi[8 * c + 1])), "r"(pack_bf16(hi[8 * c + 2], hi[8 * c + 3])),
+                             "r"(pack_bf16(hi[8 * c + 4], hi[8 * c + 5])), "r"(pack_bf16(hi[8 * c + 6], hi[8 * c + 7]))
+                             : "memory");
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (((4) ^ (lane & 7)) << 4)),
+                           "r"(hold0.x), "r"(hold0.y), "r"(hold0.z), "r"(hold0.w) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (((5) ^ (lane & 7)) << 4)),
+                           "r"(hold1.x), "r"(hold1.y), "r"(hold1.z), "r"(hold1.w) : "memory");
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_d, out_col0, m0 + ew * 32, slab);
+            ptx::tma_store_commit();
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          continue;
+        }
+      }
       if (has_sub) {
 #pragma unroll
         for (int hp = 0; hp < ACC_PER_SUB / 32; ++hp) {
@@ -261,7 +378,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
           // bias for these 32 columns: issued under the TMEM load so the two latencies overlap
           const int nb = n0 + acc_col0 + hp * 32;  // global column of v[0]
-          const bool bias_vec = !SWIGLU && p.bias != nullptr && nb + 32 <= p.N;
+          const bool use_bias = p.bias != nullptr && first_split;
+          const bool bias_vec = !SWIGLU && use_bias && nb + 32 <= p.N;
           float4 bq[8];
           if (bias_vec) {
 #pragma unroll
@@ -294,7 +412,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                            : "memory");
             }
           } else {
-            if (p.bias != nullptr) {
+            if (use_bias) {
               if (bias_vec) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -469,10 +587,11 @@ int make_tmap_f32_store(CUtensorMap* out, void* ptr, long long rows, long long c
   return 0;
 }
 
-template <int BLOCK_N, bool SWIGLU, bool OUT_F32 = false>
+template <int BLOCK_N, bool SWIGLU, bool OUT_F32 = false, bool ROPE = false>
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
+  static_assert(!ROPE || (!SWIGLU && !OUT_F32), "the RoPE epilogue is a plain bf16 epilogue");
   using Cfg = GemmCfg<BLOCK_N>;
-  auto kfn = gemm_bf16_tcgen05_kernel<BLOCK_N, SWIGLU, OUT_F32>;
+  auto kfn = gemm_bf16_tcgen05_kernel<BLOCK_N, SWIGLU, OUT_F32, ROPE>;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), Cfg::SMEM_BYTES)) return rc;
   CUtensorMap ta, tw, td;
   if (int rc = make_tmap_bf16(&ta, g.A, g.M, g.K, g.lda, BLOCK_M)) return rc;
@@ -487,9 +606,19 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   ep.M = g.M; ep.N = g.N; ep.K = g.K;
   ep.bias = g.bias; ep.row_scale = g.row_scale;
   ep.resid = static_cast<const __nv_bfloat16*>(g.resid); ep.ldr = g.ldr; ep.act = g.act; ep.ab_f16 = g.ab_f16; ep.out_f32 = g.out_f32;
+  ep.rope_tab = g.rope_tab; ep.rope_T = g.rope_T; ep.rope_cols = g.rope_cols;
   const int tiles = ceil_div(g.M, PAIR_M) * ceil_div(g.N, BLOCK_N);
   const int pairs = num_sms() / 2;
-  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  // split-K (reduce-add epilogue only): every split must own at least one k-block
+  int split = 1;
+  if (OUT_F32 && g.split_k > 1 && g.resid != nullptr) {
+    const int num_kb = ceil_div(g.K, BLOCK_K);
+    const int kb_per = ceil_div(num_kb, g.split_k < num_kb ? g.split_k : num_kb);
+    split = ceil_div(num_kb, kb_per);
+  }
+  ep.split_k = split;
+  const long long work = static_cast<long long>(tiles) * split;
+  const int grid = 2 * static_cast<int>(work < pairs ? work : pairs);
   kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tw, td, ep);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -539,6 +668,13 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
                  "fp32 output: plain / bias / activation epilogues; a residual must be D itself (in-place stream update)");
   if (g.act == ACT_GELU_HALF_F16)
     FVLA_REQUIRE(g.resid == nullptr && !g.swiglu, "the fp16-output GELU epilogue takes no residual");
+  if (g.rope_tab != nullptr)
+    FVLA_REQUIRE(g.rope_T >= 32 && g.rope_cols % 64 == 0 && g.rope_cols <= g.N && g.N % 64 == 0 && !g.swiglu &&
+                     !g.out_f32 && g.act == ACT_NONE && g.resid == nullptr && g.row_scale == nullptr,
+                 "RoPE epilogue: plain bf16 projection whose rotated columns are whole 64-wide heads, >= 32 positions");
+  if (g.split_k > 1)
+    FVLA_REQUIRE(g.out_f32 && g.resid == g.D && g.act == ACT_NONE,
+                 "split-K needs the reduce-add epilogue (fp32 D updated in place)");
   const int bn = g.block_n > 0 ? g.block_n : pick_block_n(g.M, g.N, g.swiglu != 0);
   if (g.swiglu) {
     switch (bn) {
@@ -552,6 +688,14 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
       case 192: return launch_gemm<192, false, true>(g, stream);
       case 128: return launch_gemm<128, false, true>(g, stream);
       case 64: return launch_gemm<64, false, true>(g, stream);
+      default: break;
+    }
+  } else if (g.rope_tab != nullptr) {
+    switch (bn) {
+      case 256: return launch_gemm<256, false, false, true>(g, stream);
+      case 192: return launch_gemm<192, false, false, true>(g, stream);
+      case 128: return launch_gemm<128, false, false, true>(g, stream);
+      case 64: return launch_gemm<64, false, false, true>(g, stream);
       default: break;
     }
   } else {

@@ -26,6 +26,13 @@ struct GemmArgs {
   int ab_f16 = 0;                         // bf16 path: A and W hold FP16 bits (fp16 x fp16 -> fp32 MMA)
   int out_f32 = 0;                        // bf16 path: D is FP32 (ldd in fp32 elements); resid must be null or D itself
                                           // (in-place stream update, done as a TMA reduce-add)
+  // bf16 path, Qwen2 qkv projection: rotate-half RoPE (head_dim 64) in the epilogue.  Output columns [0, rope_cols)
+  // are heads of 64 columns rotated with table row (m % rope_T); rope_tab [rope_T][32] holds (cos, sin) as packed
+  // fp16 pairs (transformers apply_rotary_pos_emb; rope_T >= 32)
+  const uint32_t* rope_tab = nullptr; int rope_T = 0, rope_cols = 0;
+  // bf16 path, out_f32 with resid == D: split the K loop over `split_k` CTA pairs per tile, every split reduce-adding
+  // its partial product into D — for small-M GEMMs whose tiles cannot fill the SMs (the b = 1 prefill)
+  int split_k = 0;
 };
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);  // tcgen05 + TMA + TMEM
 int gemm_f32(const GemmArgs& g, cudaStream_t stream);   // FFMA, fp32 parity mode
