@@ -28,3 +28,25 @@ for B, Ntok, heads in [(32, 1024, 24), (32, 256, 48)]:
     fl = 4.0 * B * heads * Ntok * Ntok * hd
     print(f"B={B} N={Ntok} heads={heads}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s  "
           f"{B * heads * Ntok * Ntok / ms / 1e6:.1f} Gscores/s  rel err {err:.2e}")
+
+# Qwen2-0.5B prefill of the batch-64 step: causal, 14 query heads on 2 kv heads, head_dim 64, T' = 272
+B, T, hq, hkv, hd = 64, 272, 14, 2, 64
+g = torch.Generator(device="cuda").manual_seed(1)
+qkv = torch.randn(B * T, (hq + 2 * hkv) * hd, device="cuda", generator=g).bfloat16()
+for _ in range(3):
+    out = N.op_attention(qkv, B, T, hq, hkv, hd, hd ** -0.5, True)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    out = N.op_attention(qkv, B, T, hq, hkv, hd, hd ** -0.5, True)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 20
+x = qkv[:T].float()
+q = x[:, : hq * hd].view(T, hq, hd).permute(1, 0, 2)
+k = x[:, hq * hd: (hq + hkv) * hd].view(T, hkv, hd).permute(1, 0, 2).repeat_interleave(hq // hkv, 0)
+v = x[:, (hq + hkv) * hd:].view(T, hkv, hd).permute(1, 0, 2).repeat_interleave(hq // hkv, 0)
+sc = (q * hd ** -0.5) @ k.transpose(-1, -2) + torch.full((T, T), float("-inf"), device="cuda").triu(1)
+ref = (torch.softmax(sc, -1) @ v).permute(1, 0, 2).reshape(T, hq * hd)
+err = float((out[:T].float() - ref).abs().max() / ref.abs().max())
+print(f"causal GQA B={B} T={T}: {ms:.4f} ms  {B * hq * T * T / 2 / ms / 1e6:.1f} Gscores/s  rel err {err:.2e}")
