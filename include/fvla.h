@@ -198,6 +198,24 @@ int fvla_op_layernorm_rows(int32_t dtype, const void* x, void* out, int32_t rows
 int fvla_op_ffn_fused(const void* x, const void* w1_half, const float* b1_half, const void* w2,
                       const float* b2, const void* resid, void* out, int32_t M, int32_t C,
                       int32_t hidden, void* stream);
+/* ---- training step of the action head (BASELINE config 3) ----------------------------------------------------
+ * What `loss.backward()` does to the head in the reference's step (training/trainer.py:168-182: compute_loss ->
+ * accelerator.backward; loss = F.mse_loss(pred, gt[:, 0]), lerobot_fastvla/modeling_fastvla.py:127-133; the backbone
+ * runs under no_grad, fastvlm_adapter.py:501): forward of the head modules of fastvla/fastvlm_with_expert.py:23-38
+ * in TRAIN mode (Dropout active), MSE loss, backward — in fp32, on the torch parameters themselves.
+ *   params[12]: DEVICE fp32 tensors in nn.Module parameter order — state_projection.0.{weight,bias},
+ *               state_projection.1.{weight,bias}, fusion.0.{weight,bias}, fusion.1.{weight,bias},
+ *               fusion.4.{weight,bias}, action_head.{weight,bias}
+ *   pooled [B,H] backbone features (fvla_forward's `pooled` output), states [B,S], target [B,A]: device fp32
+ *   keep_mask [B,F] uint8 (1 = keep) when drop_p > 0, else NULL
+ *   grads: the flat fp32 gradient buffer, same order and sizes as params (WRITTEN: this is d loss / d param, to be
+ *          all-reduced over the data-parallel ranks by the caller — it is the buffer NCCL runs over, no copy)
+ *   loss: device scalar;  actions: optional [B,A] predictions;  scratch: fvla_head_train_scratch_floats() floats */
+int64_t fvla_head_train_scratch_floats(int32_t B, int32_t H, int32_t S, int32_t Hd, int32_t F, int32_t A);
+int fvla_head_forward_backward(int32_t B, int32_t H, int32_t S, int32_t Hd, int32_t F, int32_t A,
+                               const float* const* params, const float* pooled, const float* states,
+                               const float* target, const uint8_t* keep_mask, float drop_p, float* grads, float* loss,
+                               float* actions, float* scratch, int64_t scratch_floats, void* stream);
 int fvla_op_convert(int32_t src_dtype, const void* src, int32_t dst_dtype, void* dst, int64_t n,
                     void* stream);
 

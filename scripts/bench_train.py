@@ -6,7 +6,8 @@
         scripts/bench_train.py --batch 16
 
 One step on each rank = frozen backbone forward in the CUDA engine (no_grad, as the reference:
-fastvlm_adapter.py:501) -> head forward/backward through autograd into the flat gradient buffer -> ONE all-reduce
+fastvlm_adapter.py:501) -> head forward / MSE / backward in libfvla (fvla_head_forward_backward: gradients written
+straight into the flat buffer; `--autograd` runs the head through torch autograd instead) -> ONE all-reduce
 of that buffer (NCCL) -> global-norm clip -> AdamW on the head.  The phases are timed separately with CUDA events
 on the current stream (the collective is enqueued on it by torch.distributed's wait), max over ranks, and rank 0
 prints one JSON line.
@@ -37,6 +38,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--autograd", action="store_true", help="head forward/backward through torch autograd (A/B)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench_train.py needs a CUDA device: the FastVLA B200 path has no CPU fallback")
@@ -48,7 +50,7 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=dev)
 
     from vla_fastvlm.fastvla import FastVLAConfig, FastVLAPolicy
-    from vla_fastvlm.training import HeadGradAllReduce
+    from vla_fastvlm.training import HeadGradAllReduce, NativeHeadStep
 
     cfg = FastVLAConfig(vlm_model_name=f"synthetic:{args.model}", state_dim=STATE_DIM, action_dim=ACTION_DIM,
                         compute_dtype="bfloat16", image_token_mode="prefix")
@@ -62,6 +64,7 @@ def main() -> None:
     trainable = [p for p in policy.parameters() if p.requires_grad]
     reducer = HeadGradAllReduce(trainable)
     opt = torch.optim.AdamW(trainable, lr=1e-4, weight_decay=0.01, fused=True)
+    native = None if args.autograd else NativeHeadStep(policy.model, reducer)
 
     names = ["backbone_fwd", "head_fwd_bwd", "all_reduce", "clip_adamw"]
     acc = {n: 0.0 for n in names}
@@ -72,15 +75,19 @@ def main() -> None:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        reducer.zero()
+        if native is None:
+            reducer.zero()
         ev[0].record()
         with torch.no_grad():
             feats = policy.model.backbone(batch["images"], batch["tasks"], device=dev)
         ev[1].record()
-        m = policy.model
-        fused = m.fusion(torch.cat([feats, m.state_projection(batch["states"])], dim=-1))
-        loss = torch.nn.functional.mse_loss(m.action_head(fused), batch["actions"])
-        loss.backward()
+        if native is not None:
+            loss = native(feats, batch["states"], batch["actions"], train=True)
+        else:
+            m = policy.model
+            fused = m.fusion(torch.cat([feats, m.state_projection(batch["states"])], dim=-1))
+            loss = torch.nn.functional.mse_loss(m.action_head(fused), batch["actions"])
+            loss.backward()
         ev[2].record()
         reducer.all_reduce()
         ev[3].record()
@@ -110,7 +117,7 @@ def main() -> None:
             "metric": "training step time (frozen backbone, head-only DP)", "value": step_ms, "unit": "ms/step",
             "higher_is_better": False, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "samples_per_s": args.batch * world / (step_ms / 1e3), "phases_ms": phases,
-            "allreduce_bytes": reducer.numel * 4, "loss_first": first, "loss_last": last, "dtype": "bf16 backbone, fp32 head",
+            "allreduce_bytes": reducer.numel * 4, "head_step": "autograd" if native is None else "libfvla fvla_head_forward_backward", "loss_first": first, "loss_last": last, "dtype": "bf16 backbone, fp32 head",
             "config": {"workload": f"FastVLA-{args.model.split('-')[-1]} train step, batch {args.batch}/GPU, ALOHA-shaped "
                                    "(480x640 frame letterboxed to 1024^2, 14-dim state/action)",
                        "parallelism": f"dp{world}: one all-reduce of the flat head gradient"}}), flush=True)

@@ -186,3 +186,93 @@ def test_training_step_updates_head_and_engine():
     with torch.no_grad():
         ref = pol._predict_actions(batch)                                     # autograd-path head on engine features
     assert torch.allclose(after, ref, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("drop_p", [0.0, 0.1])
+def test_native_head_forward_backward_matches_autograd(drop_p):
+    """fvla_head_forward_backward (csrc/head_train.cu) against torch autograd on the reference's head modules in
+    train mode: same loss, same twelve gradients, written into the flat all-reduce buffer (row a13)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from torch import nn
+    from torch.nn import functional as F
+
+    from vla_fastvlm.training import HeadGradAllReduce, NativeHeadStep
+
+    torch.manual_seed(0)
+    H, S, A, Hd, Fd, B = 136, 6, 5, 72, 80, 37
+
+    class Head(nn.Module):  # the head of FastVLMWithExpert (fastvla/fastvlm_with_expert.py:23-38), same attribute names
+        def __init__(self):
+            super().__init__()
+            self.state_projection = nn.Sequential(nn.LayerNorm(S), nn.Linear(S, Hd), nn.SiLU())
+            self.fusion = nn.Sequential(nn.Linear(H + Hd, Fd), nn.LayerNorm(Fd), nn.SiLU(), nn.Dropout(drop_p),
+                                        nn.Linear(Fd, Fd), nn.SiLU())
+            self.action_head = nn.Linear(Fd, A)
+
+    head = Head().cuda()
+    for p in head.parameters():  # non-trivial norm weights / biases
+        if p.ndim == 1:
+            p.data.uniform_(-0.5, 1.5)
+    params = list(head.parameters())
+    pooled, states, target = torch.randn(B, H).cuda(), torch.randn(B, S).cuda() * 2, torch.randn(B, A).cuda()
+    keep = (torch.rand(B, Fd, device="cuda") >= drop_p).to(torch.uint8)
+    # autograd with the SAME mask (Dropout replaced by the explicit mask, as nn.Dropout scales by 1/(1-p))
+    s = head.state_projection(states)
+    f = head.fusion[2](head.fusion[1](head.fusion[0](torch.cat([pooled, s], -1))))
+    if drop_p > 0:
+        f = f * keep.float() / (1.0 - drop_p)
+    pred = head.action_head(head.fusion[5](head.fusion[4](f)))
+    loss = F.mse_loss(pred, target)
+    want = torch.autograd.grad(loss, params)
+
+    red = HeadGradAllReduce(params)
+    step = NativeHeadStep(head, red)
+    red.flat.fill_(123.0)  # the kernels WRITE the gradients: no dependence on what was there
+    got_loss = step(pooled, states, target, train=True, keep_mask=keep)
+    torch.cuda.synchronize()
+    assert abs(float(got_loss) - float(loss)) <= 1e-5 * max(1.0, abs(float(loss)))
+    off = 0
+    for p, w in zip(params, want):
+        g = red.flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+        assert p.grad.data_ptr() == g.data_ptr()                       # .grad IS the slice of the flat buffer
+        scale = float(w.abs().max()) + 1e-12
+        assert float((g - w).abs().max()) <= 2e-5 * max(scale, 1e-3), (tuple(p.shape), float((g - w).abs().max()), scale)
+    assert off == red.numel
+
+
+@pytest.mark.gpu
+def test_native_training_step_through_the_plugin():
+    """train_step_native: engine backbone -> native head fwd/bwd -> flat buffer -> (world-1) all-reduce -> AdamW; the
+    loss falls and matches the autograd step's trajectory at dropout 0."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from vla_fastvlm.lerobot_fastvla import FastVLAConfig, FastVLAPolicy
+    from vla_fastvlm.training import HeadGradAllReduce, NativeHeadStep, train_step, train_step_native
+
+    inp, outp = _features(n_cam=1)
+    cfg = FastVLAConfig(input_features=inp, output_features=outp, device="cuda", vlm_model_name="synthetic:tiny",
+                        hidden_dim=TINY_HEAD["hidden_dim"], fusion_dim=TINY_HEAD["fusion_dim"], image_token_mode="prefix",
+                        dropout=0.0)
+    g = torch.Generator().manual_seed(3)
+    B = 4
+    batch = {"observation.images.cam0": torch.rand(B, 3, 96, 128, generator=g).cuda(),
+             "observation.state": torch.randn(B, 6, generator=g).cuda(), "task": ["push the block"] * B,
+             "action": torch.randn(B, 1, 5, generator=g).cuda()}
+    losses = {}
+    for mode in ("autograd", "native"):
+        torch.manual_seed(11)
+        pol = FastVLAPolicy(cfg).cuda()
+        trainable = [p for p in pol.get_optim_params() if p.requires_grad]
+        red = HeadGradAllReduce(trainable)
+        opt = torch.optim.AdamW(trainable, lr=3e-3, weight_decay=0.0)
+        if mode == "native":
+            step = NativeHeadStep(pol.model, red)
+            losses[mode] = [train_step_native(pol, batch, opt, red, step)[0] for _ in range(8)]
+        else:
+            losses[mode] = [train_step(pol, batch, opt, red)[0] for _ in range(8)]
+    assert losses["native"][-1] < 0.7 * losses["native"][0], losses
+    for a, b in zip(losses["native"], losses["autograd"]):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), losses

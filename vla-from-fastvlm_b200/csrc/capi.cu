@@ -232,6 +232,33 @@ int fvla_op_ffn_fused(const void* x, const void* w1_half, const float* b1_half, 
   return fvla::ffn_fused(a, static_cast<cudaStream_t>(stream));
 }
 
+int64_t fvla_head_train_scratch_floats(int32_t B, int32_t H, int32_t S, int32_t Hd, int32_t F, int32_t A) {
+  return static_cast<int64_t>(fvla::head_train_scratch_floats(B, H, S, Hd, F, A));
+}
+
+int fvla_head_forward_backward(int32_t B, int32_t H, int32_t S, int32_t Hd, int32_t F, int32_t A,
+                               const float* const* params, const float* pooled, const float* states,
+                               const float* target, const uint8_t* keep_mask, float drop_p, float* grads, float* loss,
+                               float* actions, float* scratch, int64_t scratch_floats, void* stream) {
+  if (params == nullptr || pooled == nullptr || states == nullptr || target == nullptr || grads == nullptr ||
+      loss == nullptr) {
+    set_error("fvla_head_forward_backward: null argument");
+    return 2;
+  }
+  for (int i = 0; i < 12; ++i)
+    if (params[i] == nullptr) { set_error("fvla_head_forward_backward: null parameter tensor"); return 2; }
+  fvla::HeadTrainArgs t;
+  t.B = B; t.H = H; t.S = S; t.Hd = Hd; t.F = F; t.A = A;
+  t.w.ln_s_w = params[0]; t.w.ln_s_b = params[1]; t.w.w_state = params[2]; t.w.b_state = params[3];
+  t.w.w_f0 = params[4]; t.w.b_f0 = params[5]; t.w.ln_f_w = params[6]; t.w.ln_f_b = params[7];
+  t.w.w_f4 = params[8]; t.w.b_f4 = params[9]; t.w.w_act = params[10]; t.w.b_act = params[11];
+  t.w.H = H; t.w.S = S; t.w.Hd = Hd; t.w.F = F; t.w.A = A;
+  t.pooled = pooled; t.states = states; t.target = target; t.keep_mask = keep_mask; t.drop_p = drop_p;
+  t.grads = grads; t.loss = loss; t.actions = actions; t.scratch = scratch;
+  t.scratch_floats = scratch_floats > 0 ? static_cast<size_t>(scratch_floats) : 0;
+  return fvla::head_train_step(t, static_cast<cudaStream_t>(stream));
+}
+
 int fvla_op_convert(int32_t src_dtype, const void* src, int32_t dst_dtype, void* dst, int64_t n,
                     void* stream) {
   return fvla::convert(src_dtype, src, dst_dtype, dst, n, static_cast<cudaStream_t>(stream));

@@ -182,6 +182,23 @@ int action_head(int dtype, const HeadWeights& w, const float* pooled, const floa
                 float* actions, float* state_feat, float* x1_scratch, float* fused, int B,
                 cudaStream_t stream);
 
+// ---- FastVLA head training step (fp32): forward + MSE + backward, gradients into a flat buffer (head_train.cu) ----
+struct HeadTrainArgs {
+  int B = 0, H = 0, S = 0, Hd = 0, F = 0, A = 0;
+  HeadWeights w{};                      // all twelve tensors as DEVICE FP32 (the torch parameters themselves)
+  const float* pooled = nullptr;        // [B, H] backbone features (no gradient: the backbone is frozen)
+  const float* states = nullptr;        // [B, S]
+  const float* target = nullptr;        // [B, A]
+  const uint8_t* keep_mask = nullptr;   // [B, F] Dropout keep mask (1 = keep) when drop_p > 0
+  float drop_p = 0.f;
+  float* grads = nullptr;               // flat, nn.Module parameter order (written, not accumulated)
+  float* loss = nullptr;                // device scalar
+  float* actions = nullptr;             // optional [B, A] predictions
+  float* scratch = nullptr; size_t scratch_floats = 0;
+};
+size_t head_train_scratch_floats(int B, int H, int S, int Hd, int F, int A);
+int head_train_step(const HeadTrainArgs& t, cudaStream_t stream);
+
 // ---- small utilities -------------------------------------------------------------------------
 int convert(int src_dtype, const void* src, int dst_dtype, void* dst, long long n, cudaStream_t s);
 int rope_table(float* cos_t, float* sin_t, int T, int head_dim, float theta, cudaStream_t s);

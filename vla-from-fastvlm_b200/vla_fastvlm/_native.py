@@ -126,6 +126,9 @@ _SIGNATURES = {
     "fvla_op_rmsnorm": (C.c_int, [_I32, _VP, _VP, _VP, _I32, _I32, _F32, _VP]),
     "fvla_op_layernorm_rows": (C.c_int, [_I32, _VP, _VP, _I32, _I32, _F32, _VP]),
     "fvla_op_ffn_fused": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP]),
+    "fvla_head_train_scratch_floats": (_I64, [_I32, _I32, _I32, _I32, _I32, _I32]),
+    "fvla_head_forward_backward": (C.c_int, [_I32, _I32, _I32, _I32, _I32, _I32, C.POINTER(_VP), _VP, _VP, _VP, _VP,
+                                             _F32, _VP, _VP, _VP, _VP, _I64, _VP]),
     "fvla_op_convert": (C.c_int, [_I32, _VP, _I32, _VP, _I64, _VP]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

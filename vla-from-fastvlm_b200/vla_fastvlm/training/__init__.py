@@ -1,4 +1,4 @@
 """Data-parallel training step of the FastVLA head (the backbone is frozen and runs in the CUDA engine)."""
-from .head_dp import HeadGradAllReduce, train_step
+from .head_dp import HeadGradAllReduce, NativeHeadStep, train_step, train_step_native
 
-__all__ = ["HeadGradAllReduce", "train_step"]
+__all__ = ["HeadGradAllReduce", "NativeHeadStep", "train_step", "train_step_native"]
