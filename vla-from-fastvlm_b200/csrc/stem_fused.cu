@@ -20,6 +20,7 @@
 #include "ptx_sm100.cuh"
 #include "tma_host.h"
 
+#include <algorithm>
 #include <cstring>
 
 namespace fvla {
@@ -39,7 +40,8 @@ constexpr int SF_IN_BYTES = SF_IH * SF_IP * 8;     // 10 080 B landed by one TMA
 constexpr int SF_C_BYTES = SF_NPX * SF_CPITCH;
 constexpr int SF_W1_BYTES = 9 * (SF_CB / 2) * 4;
 constexpr int SF_BT_BYTES = 3 * 4 * 32 * 8;       // this channel block's B fragments
-constexpr int SF_SMEM = ((SF_IN_BYTES + 15) / 16) * 16 + SF_C_BYTES + SF_W1_BYTES + SF_BT_BYTES + 16 + 128;
+constexpr int SF_IN_SLOT = ((SF_IN_BYTES + 127) / 128) * 128;   // two patch buffers: the next tile's TMA load is in flight
+constexpr int SF_SMEM = 2 * SF_IN_SLOT + SF_C_BYTES + SF_W1_BYTES + SF_BT_BYTES + 16 + 128;
 constexpr int SF_BTAB_WORDS = 3 * 4 * 32 * 2;   // per channel block: [k-step 3][n-block 4][lane 32][2]
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -66,27 +68,37 @@ __device__ __forceinline__ float2 h2f2(uint32_t h) {
   return f;
 }
 
+// PERSISTENT: a CTA keeps one channel block (its stem.0 B fragments, stem.1 taps and biases are staged once) and walks
+// the (image, tile) list with stride gridDim.x; the input patch of the NEXT tile is requested before this tile's
+// compute starts (two patch buffers, one mbarrier each), so the TMA round trip and the per-CTA prologue — which made up
+// a third of a one-tile CTA's life (ncu: 27 % issue utilisation at 4 CTAs per SM) — no longer sit on the critical path.
 __global__ void __launch_bounds__(256, 4)
 stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* __restrict__ btab,
                   const float* __restrict__ b0_half, const float* __restrict__ w1, const float* __restrict__ b1,
-                  __nv_bfloat16* __restrict__ out, int S, int C) {
+                  __nv_bfloat16* __restrict__ out, int S, int C, int tiles_per_img, int total_tiles) {
   extern __shared__ __align__(16) uint8_t smem_raw_sf[];
   uint8_t* smem_sf = smem_raw_sf + ((128u - (ptx::smem_u32(smem_raw_sf) & 127u)) & 127u);  // TMA destination alignment
-  const uint32_t s_in = ptx::smem_u32(smem_sf);
-  const uint32_t s_c = s_in + ((SF_IN_BYTES + 15) / 16) * 16;
-  uint32_t* s_w1 = reinterpret_cast<uint32_t*>(smem_sf + ((SF_IN_BYTES + 15) / 16) * 16 + SF_C_BYTES);  // [9][16] half2
-  const uint32_t s_bar = s_c + SF_C_BYTES + SF_W1_BYTES + SF_BT_BYTES;
+  const uint32_t s_in0 = ptx::smem_u32(smem_sf);
+  const uint32_t s_c = s_in0 + 2 * SF_IN_SLOT;
+  uint32_t* s_w1 = reinterpret_cast<uint32_t*>(smem_sf + 2 * SF_IN_SLOT + SF_C_BYTES);  // [9][16] half2
+  const uint32_t s_bar = s_c + SF_C_BYTES + SF_W1_BYTES + SF_BT_BYTES;  // two barriers, 8 B each
 
   const int So = S / 4, Sc = S / 2;  // final / intermediate map side
   const int tiles_x = So / SF_TW;
-  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
   const int c0 = blockIdx.y * SF_CB;
-  const int b = blockIdx.z;
-  const int xo0 = tx * SF_TW, yo0 = ty * SF_TH;
-  const int cy0 = 2 * yo0 - 1, cx0 = 2 * xo0 - 1;   // intermediate-map origin of the patch
-  const int iy0 = 2 * cy0 - 1, ix0 = 2 * cx0 - 1;   // input origin of the patch
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
+  auto request = [&](int tile, int buf) {  // thread 0: TMA load of the input patch of `tile` into buffer `buf`
+    const int bb = tile / tiles_per_img, r = tile - bb * tiles_per_img;
+    const int tyy = r / tiles_x, txx = r - tyy * tiles_x;
+    const int ix = 2 * (2 * txx * SF_TW - 1) - 1, iy = 2 * (2 * tyy * SF_TH - 1) - 1;
+    ptx::mbar_arrive_expect_tx(s_bar + 8u * buf, SF_IN_BYTES);
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(s_in0 + static_cast<uint32_t>(buf) * SF_IN_SLOT), "l"(reinterpret_cast<uint64_t>(&tmap_in)),
+        "r"((ix - 1) * 4), "r"(iy), "r"(bb), "r"(s_bar + 8u * buf)
+        : "memory");
+  };
 
   // ---- 1. input patch (4 bf16 per pixel = 8 bytes): ONE TMA load of 35 rows x 36 pixels, zero fill outside the
   // image (= conv padding).  The image is addressed as [B][S][4 S] so a row of pixels is one contiguous TMA row; the
@@ -94,12 +106,9 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* _
   // (The per-pixel load loop this replaces was 12 % of the kernel's instructions and 21 % of its stall samples.)
   if (tid == 0) {
     ptx::mbar_init(s_bar, 1);
+    ptx::mbar_init(s_bar + 8u, 1);
     ptx::fence_barrier_init();
-    ptx::mbar_arrive_expect_tx(s_bar, SF_IN_BYTES);
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(s_in), "l"(reinterpret_cast<uint64_t>(&tmap_in)), "r"((ix0 - 1) * 4), "r"(iy0), "r"(b), "r"(s_bar)
-        : "memory");
+    if (static_cast<int>(blockIdx.x) < total_tiles) request(blockIdx.x, 0);
   }
   for (int idx = tid; idx < 9 * (SF_CB / 2); idx += 256) {
     const int tap = idx / (SF_CB / 2), cp = idx % (SF_CB / 2);
@@ -124,7 +133,22 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* _
     bias0[nb][1] = __ldg(b0_half + c0 + nb * 8 + 2 * t + 1);
   }
   __syncthreads();
-  ptx::mbar_wait(s_bar, 0);  // the input patch has landed
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+  const int buf = it & 1;
+  const uint32_t s_in = s_in0 + static_cast<uint32_t>(buf) * SF_IN_SLOT;
+  const int b = tile / tiles_per_img, trem = tile - b * tiles_per_img;
+  const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+  const int xo0 = tx * SF_TW, yo0 = ty * SF_TH;
+  const int cy0 = 2 * yo0 - 1, cx0 = 2 * xo0 - 1;   // intermediate-map origin of the patch
+  // the other patch buffer was last read in the previous iteration's phase 2, which every warp has left (the
+  // __syncthreads between the phases below): request the next tile into it now
+  if (tid == 0 && tile + static_cast<int>(gridDim.x) < total_tiles) {
+    ptx::fence_proxy_async_smem();  // generic-proxy reads of that buffer (stem.0's gathers) before the TMA rewrites it
+    request(tile + gridDim.x, buf ^ 1);
+  }
+  ptx::mbar_wait(s_bar + 8u * buf, static_cast<uint32_t>(it >> 1) & 1u);  // this tile's input patch has landed
 
   // ---- 2. stem.0: 16 intermediate pixels per mma tile, pixels flattened over the 17 x 33 patch ----
   // k = 4 * tap + ci (tap = ky * 3 + kx); this lane's k pairs: taps (4s + t/2) and (4s + 2 + t/2), channels 2(t&1)..+1
@@ -255,6 +279,8 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* _
     }
     }
   }
+  __syncthreads();  // the intermediate patch is rewritten by the next tile's stem.0
+  }
 }
 
 }  // namespace
@@ -313,9 +339,15 @@ int stem_fused(const void* in, const uint32_t* btab, const float* b0_half, const
     return 1;
   }
   const int So = S / 4;
-  dim3 grid((So / SF_TW) * (So / SF_TH), C / SF_CB, B);
+  const int tiles_per_img = (So / SF_TW) * (So / SF_TH);
+  const long long total = static_cast<long long>(tiles_per_img) * B;
+  FVLA_REQUIRE(total < (1ll << 30), "stem_fused: too many tiles");
+  // persistent CTAs: 4 per SM share the 3 channel blocks, each walking the tile list with a fixed channel block
+  const int per_cb = std::max(1, (4 * num_sms()) / (C / SF_CB));
+  dim3 grid(static_cast<unsigned>(total < per_cb ? total : per_cb), C / SF_CB, 1);
   stem_fused_kernel<<<grid, 256, SF_SMEM, stream>>>(ti, btab, b0_half, w1_packed, b1,
-                                                    static_cast<__nv_bfloat16*>(out), S, C);
+                                                    static_cast<__nv_bfloat16*>(out), S, C, tiles_per_img,
+                                                    static_cast<int>(total));
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
