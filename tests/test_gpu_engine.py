@@ -145,10 +145,9 @@ def test_engine_layernorm_attention_norm(dtype):
     if dtype == torch.float32:
         assert (out - ref).abs().max().item() <= FP32_ACTION_TOL
     else:
-        # One rounding more than the BatchNorm variant per attention block (the normalised row is a bf16 GEMM
-        # operand), and x - mean cancels leading bits of bf16 inputs: measured 2.7e-2 on this random-init tiny tower,
-        # against 1.0-1.6e-2 for the BatchNorm variant.  Stages are held to the common tolerance above.
-        assert rel_err(out, ref) <= 2 * BF16_ACTION_TOL
+        # measured 0.7-1.0e-2 over three input seeds (stages 0.6-1.0e-2), the same as the BatchNorm variant; the synthetic
+        # tower keeps the norm's gain in its weight (model/synthetic.py) so the softmax logits stay O(2) in both variants
+        assert rel_err(out, ref) <= BF16_ACTION_TOL
 
 
 def test_engine_io_normalization_fp32():

@@ -754,6 +754,11 @@ ffn_fused_tmemh_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     auto drain = [&](int dl) {
       const int tile = pair_id + dl * num_pairs;
       const int m0 = tile * FPAIR_M + static_cast<int>(cta_rank) * FM;
+      if (resid_tile >= 0) {   // no GELU of this warp ran since the last drain (e.g. two chunks per tile): request now
+        if (lane == 0) request_resid(resid_tile);
+        resid_tile = -1;
+        __syncwarp();
+      }
       ptx::mbar_wait(my_rbar, static_cast<uint32_t>(dl) & 1u);    // residual tile in the slab (32 rows x 128 B, SWIZZLE_128B)
       ptx::mbar_wait(ofull, static_cast<uint32_t>(dl) & 1u);
       ptx::tc_fence_after();

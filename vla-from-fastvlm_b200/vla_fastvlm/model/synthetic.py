@@ -90,6 +90,11 @@ def synthetic_backbone_state_dict(arch: "BackboneArch", seed: int = 0,
                 r.bn(sd, base + ".norm", d)
                 if attn_norm == "layernorm":
                     del sd[base + ".norm.running_mean"], sd[base + ".norm.running_var"]
+                    # LayerNormChannel emits unit-variance rows whatever the input scale; the q/k gains below assume
+                    # O(0.2) inputs (as the BatchNorm variant delivers), so the gain lives in the norm weight.  With
+                    # unit weights the logits have std ~50, softmax is an argmax and the tower is ill-conditioned:
+                    # rounding the norm INPUT to bf16 once, inside the fp32 oracle, moves stage 4 by 12 %.
+                    sd[base + ".norm.weight"] = sd[base + ".norm.weight"] * 0.2
                 # q/k gains chosen so softmax logits have std ~2 (not one-hot, not uniform) on O(0.2) inputs
                 sd[base + ".token_mixer.qkv.weight"] = torch.cat(
                     [r.linear(d, d, 7.0), r.linear(d, d, 7.0), r.linear(d, d, 3.0)], dim=0)
