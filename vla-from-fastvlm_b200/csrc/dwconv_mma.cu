@@ -32,6 +32,8 @@
 #include "ptx_sm100.cuh"
 #include "tma_host.h"
 
+#include <cstdlib>
+
 namespace fvla {
 namespace {
 
@@ -311,6 +313,301 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-specialised pipeline, four output rows per fragment row ("R4").
+//
+// ncu of the kernel above (profiles/): L1/shared 73 % busy, tensor pipe 29 %, issue 38 %, and a fifth of all warp
+// samples waiting at the block barriers between its three phases — with two CTAs per SM the transposition (LSU),
+// tensor-core and writer phases mostly run one after the other: per tile ~2700 shared-memory cycles + ~1900 tensor
+// cycles + ~3000 issue cycles add up to the ~6800 cycles a tile takes.  Here the three phases are three groups of
+// warps of ONE persistent CTA per SM, working on three different tiles at any time (three plane buffers):
+//
+//   warp 3          TMA issuer: 19 two-row slabs per tile (own buffers, refilled as soon as a slab is transposed)
+//   warps 0-2       slabs -> planes[b]         (ldmatrix.x4.trans + 4 STS.32 per 2 rows x 8 px x 16 ch)
+//   warps 4-11      planes[b] -> 56 mma.sync per channel -> output planes (in place)
+//   warps 12-15     output planes -> HBM       (one transposing x4 load -> 16 contiguous NHWC bytes per lane)
+//
+// linked by mbarriers only (no block barrier after the prologue).  Two further changes cut the shared-memory bytes per
+// output: (i) fragment row g owns FOUR consecutive output rows (tile height 32): A tile T[j] holds image rows
+// {4g + j}, j = 0..9, and serves both output row pairs, so a channel loads 10 x 5 tiles per 1024 outputs (3.2 bytes
+// per output byte instead of 5.1), the Toeplitz fragments are fetched once per 1024 outputs and the halo shrinks from
+// 22/16 to 38/32 rows; planes keep rows of equal (y mod 4) together so the eight rows of a tile stay consecutive.
+// (ii) The writer no longer bounces through a staging buffer: ldmatrix.trans may take each of its eight rows from a
+// DIFFERENT plane, so one x4 load picks, for eight pixels, the rows of channels {8q + 2i, 8q + 2i + 1} and every lane
+// ends up with the sixteen contiguous NHWC bytes (eight channels) of one pixel.
+// 16 channels per tile (32-byte pixels, SWIZZLE_32B slabs) keep a plane buffer at 48 KB.
+namespace r4 {
+constexpr int CB = 16;
+constexpr int TH = 32, IH = TH + 6, NSLAB = IH / 2;
+constexpr int NB = 4, TW = 8 * NB, IW = TW + 8, XB = IW / 8;
+constexpr int ROW_B = IW * 2;                                   // 80 B: an odd number of 16-byte units
+constexpr int PLANE_W = IH * ROW_B / 4 + 4;                     // 764 words = 4 (mod 8)
+constexpr int PLANE_B = PLANE_W * 4;
+constexpr int OCTET_SKEW = 64;                                  // bytes added to the planes of channels 8..15 (writer banks)
+constexpr int PLANES_B = (CB * PLANE_B + OCTET_SKEW + 127) / 128 * 128;
+constexpr int NBUF = 3;
+constexpr int SLAB_B = 2 * IW * CB * 2;                         // 2 rows x 40 px x 32 B
+constexpr int SLABS_B = (NSLAB * SLAB_B + 1023) / 1024 * 1024;  // every slab of a tile has its own buffer
+constexpr int WTAB_B = CB * WTAB_WORDS * 4;
+constexpr int BAR_B = 512;
+constexpr int SMEM_B = SLABS_B + NBUF * (PLANES_B + WTAB_B) + BAR_B + 1024;
+constexpr int P_WARPS = 3, W_WARPS = 4, M_WARPS = 16;            // + 1 TMA issuer; warpgroups: {P, P, P, issuer} {W x 4} {M x 16}
+constexpr int LIGHT_WARPS = P_WARPS + 1 + W_WARPS;
+constexpr int WS_THREADS = (LIGHT_WARPS + M_WARPS) * 32;
+constexpr int LIGHT_REGS = 48, M_REGS = 96;                        // setmaxnreg: 768 threads launch with 80 registers each
+static_assert(LIGHT_WARPS % 4 == 0 && M_WARPS % 4 == 0, "setmaxnreg works on aligned groups of four warps");
+static_assert(LIGHT_WARPS * (80 - LIGHT_REGS) >= M_WARPS * (M_REGS - 80), "register pool");
+static_assert((ROW_B / 16) % 2 == 1 && PLANE_W % 8 == 4 && SLAB_B % 256 == 0, "bank layout");
+static_assert(SMEM_B <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+static_assert(M_WARPS == CB && 8 * (2 * NSLAB + 4 * NBUF) <= BAR_B, "roles");
+
+// physical plane row of tile-local input row y: rows of equal (y mod 4) are consecutive (class sizes 10, 10, 9, 9)
+__device__ __forceinline__ int plane_row(int y) {
+  const int q = y & 3;
+  return q * 10 - (q == 3 ? 1 : 0) + (y >> 2);
+}
+__device__ __forceinline__ uint32_t plane_base(uint32_t planes, int ch) {
+  return planes + static_cast<uint32_t>(ch * PLANE_B + (ch >> 3) * OCTET_SKEW);
+}
+
+struct TileCoord { int c0, x0, y0, b; };
+__device__ __forceinline__ TileCoord decode_tile(int id, int n_cblk, int tiles_x, int tiles_y) {
+  TileCoord tc;
+  tc.c0 = (id % n_cblk) * CB;
+  id /= n_cblk;
+  tc.x0 = (id % tiles_x) * TW;
+  id /= tiles_x;
+  tc.y0 = (id % tiles_y) * TH;
+  tc.b = id / tiles_y;
+  return tc;
+}
+
+// tensor-core role of the kernel below (one channel per warp); a function of its own so that it is compiled against
+// the register budget its setmaxnreg.inc grants
+__device__ __forceinline__ void dw7_tensor_role(uint32_t planes0, uint32_t wtab0, uint32_t bars,
+                                                const float* __restrict__ bias, int n_cblk, int total_tiles) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int lj = lane >> 3, lr = lane & 7;
+  auto planes_full = [&](uint32_t b) { return bars + 8u * (2 * NSLAB + b); };
+  auto out_full = [&](uint32_t b) { return bars + 8u * (2 * NSLAB + NBUF + b); };
+  auto wtab_full = [&](uint32_t b) { return bars + 8u * (2 * NSLAB + 3 * NBUF + b); };
+  {
+    // ===================== tensor cores: one channel per warp =====================
+    const int ch = warp - LIGHT_WARPS;
+    // Toeplitz B fragment of kernel row ky (same table as the kernel above)
+    const int i0 = 2 * t - g + 1, i1 = i0 + 8;
+    const uint32_t o0 = static_cast<uint32_t>((i0 >= 0 && i0 <= 7) ? i0 : 8) * 4u;
+    const uint32_t o1 = static_cast<uint32_t>((i1 >= 0 && i1 <= 7) ? i1 : 8) * 4u;
+    // ldmatrix row address of this lane for A tiles j = jb + (lane >> 3), row (lane & 7) of the tile
+    uint32_t a_off[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int j = q < 2 ? 4 * q + lj : 8 + (lj & 1);   // third load: tiles 8, 9 of TWO pixel blocks (lj >> 1)
+      a_off[q] = static_cast<uint32_t>((plane_row(j) + lr) * ROW_B + (q == 2 ? (lj >> 1) * 16 : 0));
+    }
+    const uint32_t o_off = static_cast<uint32_t>(4 * g * ROW_B + t * 4);
+    uint32_t n = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
+      const int c0 = (tile % n_cblk) * CB;
+      const uint32_t b = n % NBUF, k = n / NBUF;
+      const float bv = __ldg(bias + c0 + ch);
+      const uint32_t plane = plane_base(planes0 + b * PLANES_B, ch);
+      const uint32_t wrow = wtab0 + b * WTAB_B + ch * (WTAB_WORDS * 4);
+      ptx::mbar_wait(wtab_full(b), k & 1u);
+      uint32_t b0[7], b1[7];
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky) {
+        b0[ky] = lds32(wrow + ky * 36 + o0);
+        b1[ky] = lds32(wrow + ky * 36 + o1);
+      }
+      ptx::mbar_wait(planes_full(b), k & 1u);
+      uint32_t T[10][XB];
+#pragma unroll
+      for (int xb = 0; xb < XB; ++xb) {
+        uint32_t lo[4], hi[4];
+        ldsm_x4(lo, plane + a_off[0] + xb * 16);
+        ldsm_x4(hi, plane + a_off[1] + xb * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { T[j][xb] = lo[j]; T[4 + j][xb] = hi[j]; }
+      }
+      uint32_t packed[2][NB][2];
+#pragma unroll
+      for (int ip = 0; ip < 2; ++ip) {
+        if (ip == 1) {   // tiles 8, 9 are first needed by the second row pair: loaded late to keep registers down
+#pragma unroll
+          for (int xb = 0; xb < XB; xb += 2) {
+            uint32_t e[4];
+            // the second pixel block of the last (odd) pair re-reads block XB-1: harmless
+            ldsm_x4(e, plane + a_off[2] + (xb + 1 < XB ? xb * 16 : (xb - (lj >> 1)) * 16));
+            T[8][xb] = e[0]; T[9][xb] = e[1];
+            if (xb + 1 < XB) { T[8][xb + 1] = e[2]; T[9][xb + 1] = e[3]; }
+          }
+        }
+        float acc[NB][4];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[nb][e] = bv;
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb)
+            mma_bf16_16816(acc[nb], T[2 * ip + ky][nb], T[2 * ip + ky + 1][nb], T[2 * ip + ky][nb + 1],
+                           T[2 * ip + ky + 1][nb + 1], b0[ky], b1[ky]);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          packed[ip][nb][0] = pack2(acc[nb][0], acc[nb][1]);
+          packed[ip][nb][1] = pack2(acc[nb][2], acc[nb][3]);
+        }
+      }
+      // this warp is the only reader of plane `ch`: once its tiles are in registers the plane takes the outputs
+      // (natural row order, 80-byte rows, 16-byte chunk index XOR (y >> 3): conflict-free for the fragment stores)
+      __syncwarp();
+#pragma unroll
+      for (int ip = 0; ip < 2; ++ip)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t orow = plane + o_off + (2 * ip + h) * ROW_B;
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) sts32(orow + ((nb ^ (g >> 1)) << 4), packed[ip][nb][h]);
+        }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(out_full(b));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* __restrict__ wtab,
+                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int C,
+                      int tiles_x, int tiles_y, int n_cblk, int total_tiles) {
+  extern __shared__ uint8_t smem_dwm[];
+  const uint32_t base = (ptx::smem_u32(smem_dwm) + 1023u) & ~1023u;
+  const uint32_t slabs = base;
+  const uint32_t planes0 = slabs + SLABS_B;
+  const uint32_t wtab0 = planes0 + NBUF * PLANES_B;
+  const uint32_t bars = wtab0 + NBUF * WTAB_B;
+  auto slab_full = [&](int s) { return bars + 8u * s; };
+  auto slab_empty = [&](int s) { return bars + 8u * (NSLAB + s); };
+  auto planes_full = [&](uint32_t b) { return bars + 8u * (2 * NSLAB + b); };
+  auto out_full = [&](uint32_t b) { return bars + 8u * (2 * NSLAB + NBUF + b); };
+  auto planes_empty = [&](uint32_t b) { return bars + 8u * (2 * NSLAB + 2 * NBUF + b); };
+  auto wtab_full = [&](uint32_t b) { return bars + 8u * (2 * NSLAB + 3 * NBUF + b); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int lj = lane >> 3, lr = lane & 7;
+
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tmap_in);
+    for (int s = 0; s < NSLAB; ++s) {
+      ptx::mbar_init(slab_full(s), 1);
+      ptx::mbar_init(slab_empty(s), 1);
+    }
+    for (uint32_t b = 0; b < NBUF; ++b) {
+      ptx::mbar_init(planes_full(b), P_WARPS);
+      ptx::mbar_init(out_full(b), M_WARPS);
+      ptx::mbar_init(planes_empty(b), W_WARPS);
+      ptx::mbar_init(wtab_full(b), 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp >= LIGHT_WARPS) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(M_REGS));
+    dw7_tensor_role(planes0, wtab0, bars, bias, n_cblk, total_tiles);
+    return;
+  }
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LIGHT_REGS));
+  if (warp == P_WARPS) {
+    // ===================== TMA issuer =====================
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
+        const TileCoord tc = decode_tile(tile, n_cblk, tiles_x, tiles_y);
+        const uint32_t b = n % NBUF, k = n / NBUF;
+        ptx::mbar_wait(out_full(b), (k & 1u) ^ 1u);       // the tensor-core warps of tile n-3 are done with wtab[b]
+        ptx::mbar_arrive_expect_tx(wtab_full(b), WTAB_B);
+        bulk_g2s(wtab0 + b * WTAB_B, wtab + static_cast<size_t>(tc.c0) * WTAB_WORDS, WTAB_B, wtab_full(b));
+#pragma unroll 1
+        for (int s = 0; s < NSLAB; ++s) {
+          ptx::mbar_wait(slab_empty(s), (n & 1u) ^ 1u);
+          ptx::mbar_arrive_expect_tx(slab_full(s), SLAB_B);
+          tma_load_4d(slabs + s * SLAB_B, &tmap_in, tc.c0, tc.x0 - 3, tc.y0 - 3 + 2 * s, tc.b, slab_full(s));
+        }
+      }
+    }
+  } else if (warp < P_WARPS) {
+    // ===================== NHWC slabs -> per-channel planes =====================
+    // x4 matrix i = lane >> 3: slab row i >> 1, channel octet i & 1; this lane addresses pixel (lane & 7) of the block
+    const int mrow = lj >> 1, cv = lj & 1;
+    uint32_t src_off[XB], dst_off[XB];
+#pragma unroll
+    for (int xb = 0; xb < XB; ++xb) {
+      const int px = mrow * IW + xb * 8 + lr;
+      src_off[xb] = static_cast<uint32_t>(px * 32 + ((cv ^ ((px >> 2) & 1)) << 4));
+      dst_off[xb] = static_cast<uint32_t>((xb * 4 + t) * 4);
+    }
+    const uint32_t ch_off0 = static_cast<uint32_t>(g * PLANE_B);
+    const uint32_t ch_off1 = static_cast<uint32_t>((8 + g) * PLANE_B + OCTET_SKEW);
+    uint32_t n = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
+      const uint32_t b = n % NBUF, k = n / NBUF;
+      const uint32_t planes = planes0 + b * PLANES_B;
+      ptx::mbar_wait(planes_empty(b), (k & 1u) ^ 1u);
+#pragma unroll 1
+      for (int s = warp; s < NSLAB; s += P_WARPS) {
+        ptx::mbar_wait(slab_full(s), n & 1u);
+        const uint32_t slab = slabs + s * SLAB_B;
+        const uint32_t r0 = planes + static_cast<uint32_t>(plane_row(2 * s) * ROW_B);
+        const uint32_t r1 = planes + static_cast<uint32_t>(plane_row(2 * s + 1) * ROW_B);
+        uint32_t R[XB][4];   // all five loads in flight before the first store (one shared-memory latency per slab)
+#pragma unroll
+        for (int xb = 0; xb < XB; ++xb) ldsm_x4_trans(R[xb], slab + src_off[xb]);
+#pragma unroll
+        for (int xb = 0; xb < XB; ++xb) {
+          sts32(r0 + ch_off0 + dst_off[xb], R[xb][0]);
+          sts32(r0 + ch_off1 + dst_off[xb], R[xb][1]);
+          sts32(r1 + ch_off0 + dst_off[xb], R[xb][2]);
+          sts32(r1 + ch_off1 + dst_off[xb], R[xb][3]);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(slab_empty(s));
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(planes_full(b));
+    }
+  } else {
+    // ===================== writer: output planes -> NHWC =====================
+    // matrix i = lane >> 3 holds the channel pair 2i, 2i+1 of each octet; its row r = lane & 7 is
+    // (channel 8*((r >> 1) & 1) + 2i + (r & 1), pixel block +2*(r >> 2)); task = (row, pixel blocks {xb0, xb0+2})
+    const int ww = warp - (P_WARPS + 1);
+    const int w_ch = 8 * ((lr >> 1) & 1) + 2 * lj + (lr & 1), w_pb = 2 * (lr >> 2);
+    const int pb = 2 * (t >> 1), oct = t & 1;
+    uint32_t n = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
+      const TileCoord tc = decode_tile(tile, n_cblk, tiles_x, tiles_y);
+      const uint32_t b = n % NBUF, k = n / NBUF;
+      const uint32_t w_plane = plane_base(planes0 + b * PLANES_B, w_ch);
+      __nv_bfloat16* obase = out + ((static_cast<size_t>(tc.b) * H + tc.y0) * W + tc.x0 + pb * 8 + g) * C + tc.c0 + oct * 8;
+      ptx::mbar_wait(out_full(b), k & 1u);
+#pragma unroll 4
+      for (int task = ww; task < TH * 2; task += W_WARPS) {
+        const int y = task >> 1, xb0 = task & 1;
+        uint32_t R[4];
+        ldsm_x4_trans(R, w_plane + y * ROW_B + (((xb0 + w_pb) ^ ((y >> 3) & 3)) << 4));
+        *reinterpret_cast<uint4*>(obase + (static_cast<size_t>(y) * W + xb0 * 8) * C) = make_uint4(R[0], R[1], R[2], R[3]);
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(planes_empty(b));
+    }
+  }
+}
+}  // namespace r4
+
 // word i (0..8) of kernel row ky for channel c: (w[ky][i-1], w[ky][i]) as bf16, zero outside 0..6
 __global__ void dwconv7_wtab_kernel(const float* __restrict__ w, int C, uint32_t* __restrict__ wtab) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -326,7 +623,8 @@ __global__ void dwconv7_wtab_kernel(const float* __restrict__ w, int C, uint32_t
   wtab[idx] = v;
 }
 
-int make_tmap_nhwc(CUtensorMap* out, const void* ptr, int B, int H, int W, int C, int box_w, int box_h) {
+int make_tmap_nhwc(CUtensorMap* out, const void* ptr, int B, int H, int W, int C, int box_w, int box_h,
+                   int box_c = CB, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_64B) {
   TmaEncodeTiledFn fn = tma_encode_fn();
   FVLA_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   FVLA_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "TMA base must be 16-byte aligned");
@@ -334,10 +632,10 @@ int make_tmap_nhwc(CUtensorMap* out, const void* ptr, int B, int H, int W, int C
                         static_cast<cuuint64_t>(B)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
                            static_cast<cuuint64_t>(H) * W * C * 2};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(CB), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1u};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1u};
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (NHWC) failed with CUresult " + std::to_string(static_cast<int>(r)));
@@ -365,6 +663,23 @@ int launch_mma(const void* in, const uint32_t* wtab, const float* bias, void* ou
   return 0;
 }
 
+int launch_mma_r4(const void* in, const uint32_t* wtab, const float* bias, void* out, int B, int H, int W, int C,
+                  cudaStream_t stream) {
+  auto kfn = r4::dwconv7_mma_r4_kernel;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), r4::SMEM_B)) return rc;
+  CUtensorMap ti;
+  if (int rc = make_tmap_nhwc(&ti, in, B, H, W, C, r4::IW, 2, r4::CB, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+  const int tiles_x = W / r4::TW, tiles_y = H / r4::TH, n_cblk = C / r4::CB;
+  const long long total = static_cast<long long>(tiles_x) * tiles_y * n_cblk * B;
+  FVLA_REQUIRE(total < (1ll << 31), "dwconv7_mma: too many tiles");
+  const int resident = num_sms();   // one warp-specialised CTA per SM
+  const int grid = total < resident ? static_cast<int>(total) : resident;
+  kfn<<<grid, r4::WS_THREADS, r4::SMEM_B, stream>>>(ti, wtab, bias, static_cast<__nv_bfloat16*>(out), H, W, C, tiles_x,
+                                             tiles_y, n_cblk, static_cast<int>(total));
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 bool dwconv7_mma_supported(int dtype, int H, int W, int C, int mult, int k, int stride, int act) {
@@ -383,6 +698,9 @@ int dwconv7_mma_prepare(const float* w_packed, int C, uint32_t* wtab, cudaStream
 
 int dwconv7_mma(const void* in, const uint32_t* wtab, const float* bias, void* out, int B, int H, int W, int C,
                 cudaStream_t stream) {
+  static const bool r4_on = std::getenv("FVLA_DISABLE_DWCONV7_R4") == nullptr;  // A/B switch for profiling
+  if (r4_on && W % r4::TW == 0 && H % r4::TH == 0 && C % r4::CB == 0)
+    return launch_mma_r4(in, wtab, bias, out, B, H, W, C, stream);
   if (W % 32 == 0) return launch_mma<4>(in, wtab, bias, out, B, H, W, C, stream);
   return launch_mma<2>(in, wtab, bias, out, B, H, W, C, stream);
 }
