@@ -1,3 +1,1 @@
-for sw in NONE TC_ATTN FUSED_FFN DWCONV_MMA DWCONV_TILED DWCONV3_TMA; do
-  echo "== disable $sw"; env FVLA_DISABLE_$sw=1 python scripts/diag_ln.py 2>&1 | tail -6
-done
+for d in 0 1 2 4 3 5 6 7; do echo "debug=$d"; FVLA_DW7_DEBUG=$d python scripts/bench_ops.py --what dwconv --batch 32 2>&1 | sed -n 3p; done

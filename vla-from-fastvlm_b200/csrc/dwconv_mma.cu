@@ -339,7 +339,8 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* 
 // 16 channels per tile (32-byte pixels, SWIZZLE_32B slabs) keep a plane buffer at 48 KB.
 namespace r4 {
 constexpr int CB = 16;
-constexpr int TH = 32, IH = TH + 6, NSLAB = IH / 2;
+constexpr int TH = 32, IH = TH + 6;
+constexpr int SROWS = 8, NSLAB = (IH + SROWS - 1) / SROWS, NPAIR = IH / 2;   // TMA slabs of 8 rows (the last: 6 + 2 unused)
 constexpr int NB = 4, TW = 8 * NB, IW = TW + 8, XB = IW / 8;
 constexpr int ROW_B = IW * 2;                                   // 80 B: an odd number of 16-byte units
 constexpr int PLANE_W = IH * ROW_B / 4 + 4;                     // 764 words = 4 (mod 8)
@@ -347,19 +348,21 @@ constexpr int PLANE_B = PLANE_W * 4;
 constexpr int OCTET_SKEW = 64;                                  // bytes added to the planes of channels 8..15 (writer banks)
 constexpr int PLANES_B = (CB * PLANE_B + OCTET_SKEW + 127) / 128 * 128;
 constexpr int NBUF = 3;
-constexpr int SLAB_B = 2 * IW * CB * 2;                         // 2 rows x 40 px x 32 B
+constexpr int SLAB_B = SROWS * IW * CB * 2;                     // 8 rows x 40 px x 32 B
 constexpr int SLABS_B = (NSLAB * SLAB_B + 1023) / 1024 * 1024;  // every slab of a tile has its own buffer
 constexpr int WTAB_B = CB * WTAB_WORDS * 4;
 constexpr int BAR_B = 512;
-constexpr int SMEM_B = SLABS_B + NBUF * (PLANES_B + WTAB_B) + BAR_B + 1024;
 constexpr int P_WARPS = 3, W_WARPS = 4, M_WARPS = 16;            // + 1 TMA issuer; warpgroups: {P, P, P, issuer} {W x 4} {M x 16}
 constexpr int LIGHT_WARPS = P_WARPS + 1 + W_WARPS;
 constexpr int WS_THREADS = (LIGHT_WARPS + M_WARPS) * 32;
+constexpr int STAGE_ROWS = 2, STAGE_B = STAGE_ROWS * TW * CB * 2;  // writer staging slice: 2 rows x 32 px x 32 B of NHWC output, two per warp
+constexpr int SMEM_B = SLABS_B + NBUF * (PLANES_B + WTAB_B) + 2 * W_WARPS * STAGE_B + BAR_B + 1024;
 constexpr int LIGHT_REGS = 48, M_REGS = 96;                        // setmaxnreg: 768 threads launch with 80 registers each
 static_assert(LIGHT_WARPS % 4 == 0 && M_WARPS % 4 == 0, "setmaxnreg works on aligned groups of four warps");
 static_assert(LIGHT_WARPS * (80 - LIGHT_REGS) >= M_WARPS * (M_REGS - 80), "register pool");
-static_assert((ROW_B / 16) % 2 == 1 && PLANE_W % 8 == 4 && SLAB_B % 256 == 0, "bank layout");
 static_assert(SMEM_B <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+static_assert(TH == 4 * W_WARPS * STAGE_ROWS, "each writer warp stores four 2-row slices of a tile");
+static_assert((ROW_B / 16) % 2 == 1 && PLANE_W % 8 == 4 && SLAB_B % 256 == 0, "bank layout");
 static_assert(M_WARPS == CB && 8 * (2 * NSLAB + 4 * NBUF) <= BAR_B, "roles");
 
 // physical plane row of tile-local input row y: rows of equal (y mod 4) are consecutive (class sizes 10, 10, 9, 9)
@@ -386,7 +389,7 @@ __device__ __forceinline__ TileCoord decode_tile(int id, int n_cblk, int tiles_x
 // tensor-core role of the kernel below (one channel per warp); a function of its own so that it is compiled against
 // the register budget its setmaxnreg.inc grants
 __device__ __forceinline__ void dw7_tensor_role(uint32_t planes0, uint32_t wtab0, uint32_t bars,
-                                                const float* __restrict__ bias, int n_cblk, int total_tiles) {
+                                                const float* __restrict__ bias, int n_cblk, int total_tiles, int debug) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int lj = lane >> 3, lr = lane & 7;
@@ -400,13 +403,15 @@ __device__ __forceinline__ void dw7_tensor_role(uint32_t planes0, uint32_t wtab0
     const int i0 = 2 * t - g + 1, i1 = i0 + 8;
     const uint32_t o0 = static_cast<uint32_t>((i0 >= 0 && i0 <= 7) ? i0 : 8) * 4u;
     const uint32_t o1 = static_cast<uint32_t>((i1 >= 0 && i1 <= 7) ? i1 : 8) * 4u;
-    // ldmatrix row address of this lane for A tiles j = jb + (lane >> 3), row (lane & 7) of the tile
-    uint32_t a_off[3];
+    // One x4 load = one A operand, no register shuffling: matrices (J, nb), (J+1, nb), (J, nb+1), (J+1, nb+1) for EVEN J.
+    // Fragment row g owns output rows 4g .. 4g+3.  The quad of tile rows (J, J+1) times kernel row ky lands on the output
+    // row pair starting at J - ky, so even kernel rows feed the pairs (0,1) and (2,3) and odd ones the pairs (1,2),
+    // (-1,0) and (3,4), whose out-of-range halves are dropped: 17 instead of 14 mma per 8-pixel block, but each is fed by
+    // one of 5 loads instead of four register moves (SASS of the shuffling version: 220 moves for 56 mma).
+    uint32_t a_off[5];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int j = q < 2 ? 4 * q + lj : 8 + (lj & 1);   // third load: tiles 8, 9 of TWO pixel blocks (lj >> 1)
-      a_off[q] = static_cast<uint32_t>((plane_row(j) + lr) * ROW_B + (q == 2 ? (lj >> 1) * 16 : 0));
-    }
+    for (int q = 0; q < 5; ++q)
+      a_off[q] = static_cast<uint32_t>((plane_row(2 * q + (lj & 1)) + lr) * ROW_B + (lj >> 1) * 16);
     const uint32_t o_off = static_cast<uint32_t>(4 * g * ROW_B + t * 4);
     uint32_t n = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
@@ -423,56 +428,46 @@ __device__ __forceinline__ void dw7_tensor_role(uint32_t planes0, uint32_t wtab0
         b1[ky] = lds32(wrow + ky * 36 + o1);
       }
       ptx::mbar_wait(planes_full(b), k & 1u);
-      uint32_t T[10][XB];
+      if (debug & 1) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(out_full(b)); continue; }
+      uint32_t packed[NB][4];   // [pixel block][output row 4g + i]
 #pragma unroll
-      for (int xb = 0; xb < XB; ++xb) {
-        uint32_t lo[4], hi[4];
-        ldsm_x4(lo, plane + a_off[0] + xb * 16);
-        ldsm_x4(hi, plane + a_off[1] + xb * 16);
+      for (int h2 = 0; h2 < NB / 2; ++h2) {
+        float E0[2][4], E2[2][4], O1[2][4], Om[2][4], O3[2][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { T[j][xb] = lo[j]; T[4 + j][xb] = hi[j]; }
-      }
-      uint32_t packed[2][NB][2];
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int ip = 0; ip < 2; ++ip) {
-        if (ip == 1) {   // tiles 8, 9 are first needed by the second row pair: loaded late to keep registers down
+          for (int e = 0; e < 4; ++e) { E0[u][e] = bv; E2[u][e] = bv; O1[u][e] = 0.f; Om[u][e] = 0.f; O3[u][e] = 0.f; }
 #pragma unroll
-          for (int xb = 0; xb < XB; xb += 2) {
-            uint32_t e[4];
-            // the second pixel block of the last (odd) pair re-reads block XB-1: harmless
-            ldsm_x4(e, plane + a_off[2] + (xb + 1 < XB ? xb * 16 : (xb - (lj >> 1)) * 16));
-            T[8][xb] = e[0]; T[9][xb] = e[1];
-            if (xb + 1 < XB) { T[8][xb + 1] = e[2]; T[9][xb + 1] = e[3]; }
+        for (int q = 0; q < 5; ++q) {
+          const int J = 2 * q;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            uint32_t A[4];
+            ldsm_x4(A, plane + a_off[q] + (2 * h2 + u) * 16);
+            if (J <= 6) mma_bf16_16816(E0[u], A[0], A[1], A[2], A[3], b0[J > 6 ? 0 : J], b1[J > 6 ? 0 : J]);
+            if (J >= 2) mma_bf16_16816(E2[u], A[0], A[1], A[2], A[3], b0[J >= 2 ? J - 2 : 0], b1[J >= 2 ? J - 2 : 0]);
+            if (J >= 2 && J <= 6) mma_bf16_16816(O1[u], A[0], A[1], A[2], A[3], b0[J >= 2 && J <= 6 ? J - 1 : 0], b1[J >= 2 && J <= 6 ? J - 1 : 0]);
+            if (J <= 4) mma_bf16_16816(Om[u], A[0], A[1], A[2], A[3], b0[J <= 4 ? J + 1 : 0], b1[J <= 4 ? J + 1 : 0]);
+            if (J >= 4) mma_bf16_16816(O3[u], A[0], A[1], A[2], A[3], b0[J >= 4 ? J - 3 : 0], b1[J >= 4 ? J - 3 : 0]);
           }
         }
-        float acc[NB][4];
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[nb][e] = bv;
-#pragma unroll
-        for (int ky = 0; ky < 7; ++ky)
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb)
-            mma_bf16_16816(acc[nb], T[2 * ip + ky][nb], T[2 * ip + ky + 1][nb], T[2 * ip + ky][nb + 1],
-                           T[2 * ip + ky + 1][nb + 1], b0[ky], b1[ky]);
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          packed[ip][nb][0] = pack2(acc[nb][0], acc[nb][1]);
-          packed[ip][nb][1] = pack2(acc[nb][2], acc[nb][3]);
+        for (int u = 0; u < 2; ++u) {
+          packed[2 * h2 + u][0] = pack2(E0[u][0] + Om[u][2], E0[u][1] + Om[u][3]);
+          packed[2 * h2 + u][1] = pack2(E0[u][2] + O1[u][0], E0[u][3] + O1[u][1]);
+          packed[2 * h2 + u][2] = pack2(E2[u][0] + O1[u][2], E2[u][1] + O1[u][3]);
+          packed[2 * h2 + u][3] = pack2(E2[u][2] + O3[u][0], E2[u][3] + O3[u][1]);
         }
       }
       // this warp is the only reader of plane `ch`: once its tiles are in registers the plane takes the outputs
       // (natural row order, 80-byte rows, 16-byte chunk index XOR (y >> 3): conflict-free for the fragment stores)
       __syncwarp();
 #pragma unroll
-      for (int ip = 0; ip < 2; ++ip)
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t orow = plane + o_off + i * ROW_B;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t orow = plane + o_off + (2 * ip + h) * ROW_B;
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb) sts32(orow + ((nb ^ (g >> 1)) << 4), packed[ip][nb][h]);
-        }
+        for (int nb = 0; nb < NB; ++nb) sts32(orow + ((nb ^ (g >> 1)) << 4), packed[nb][i]);
+      }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(out_full(b));
     }
@@ -480,13 +475,14 @@ __device__ __forceinline__ void dw7_tensor_role(uint32_t planes0, uint32_t wtab0
 }
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
-dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* __restrict__ wtab,
-                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int C,
-                      int tiles_x, int tiles_y, int n_cblk, int total_tiles) {
+dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
+                      const uint32_t* __restrict__ wtab, const float* __restrict__ bias, int H, int W, int C,
+                      int tiles_x, int tiles_y, int n_cblk, int total_tiles, int debug) {
   extern __shared__ uint8_t smem_dwm[];
   const uint32_t base = (ptx::smem_u32(smem_dwm) + 1023u) & ~1023u;
   const uint32_t slabs = base;
-  const uint32_t planes0 = slabs + SLABS_B;
+  const uint32_t stage0 = slabs + SLABS_B;
+  const uint32_t planes0 = stage0 + 2 * W_WARPS * STAGE_B;
   const uint32_t wtab0 = planes0 + NBUF * PLANES_B;
   const uint32_t bars = wtab0 + NBUF * WTAB_B;
   auto slab_full = [&](int s) { return bars + 8u * s; };
@@ -502,9 +498,10 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_
 
   if (tid == 0) {
     ptx::prefetch_tmap(&tmap_in);
+    ptx::prefetch_tmap(&tmap_out);
     for (int s = 0; s < NSLAB; ++s) {
       ptx::mbar_init(slab_full(s), 1);
-      ptx::mbar_init(slab_empty(s), 1);
+      ptx::mbar_init(slab_empty(s), (IH - SROWS * s < SROWS ? IH - SROWS * s : SROWS) / 2);   // one arrival per row pair
     }
     for (uint32_t b = 0; b < NBUF; ++b) {
       ptx::mbar_init(planes_full(b), P_WARPS);
@@ -518,7 +515,7 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_
 
   if (warp >= LIGHT_WARPS) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(M_REGS));
-    dw7_tensor_role(planes0, wtab0, bars, bias, n_cblk, total_tiles);
+    dw7_tensor_role(planes0, wtab0, bars, bias, n_cblk, total_tiles, debug);
     return;
   }
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LIGHT_REGS));
@@ -536,7 +533,7 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_
         for (int s = 0; s < NSLAB; ++s) {
           ptx::mbar_wait(slab_empty(s), (n & 1u) ^ 1u);
           ptx::mbar_arrive_expect_tx(slab_full(s), SLAB_B);
-          tma_load_4d(slabs + s * SLAB_B, &tmap_in, tc.c0, tc.x0 - 3, tc.y0 - 3 + 2 * s, tc.b, slab_full(s));
+          tma_load_4d(slabs + s * SLAB_B, &tmap_in, tc.c0, tc.x0 - 3, tc.y0 - 3 + SROWS * s, tc.b, slab_full(s));
         }
       }
     }
@@ -559,12 +556,14 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_
       const uint32_t planes = planes0 + b * PLANES_B;
       ptx::mbar_wait(planes_empty(b), (k & 1u) ^ 1u);
 #pragma unroll 1
-      for (int s = warp; s < NSLAB; s += P_WARPS) {
+      for (int rp = warp; rp < NPAIR; rp += P_WARPS) {   // task = one row pair of a slab
+        const int s = rp / (SROWS / 2);
         ptx::mbar_wait(slab_full(s), n & 1u);
-        const uint32_t slab = slabs + s * SLAB_B;
-        const uint32_t r0 = planes + static_cast<uint32_t>(plane_row(2 * s) * ROW_B);
-        const uint32_t r1 = planes + static_cast<uint32_t>(plane_row(2 * s + 1) * ROW_B);
-        uint32_t R[XB][4];   // all five loads in flight before the first store (one shared-memory latency per slab)
+        const uint32_t slab = slabs + s * SLAB_B + (rp % (SROWS / 2)) * (2 * IW * CB * 2);
+        const uint32_t r0 = planes + static_cast<uint32_t>(plane_row(2 * rp) * ROW_B);
+        const uint32_t r1 = planes + static_cast<uint32_t>(plane_row(2 * rp + 1) * ROW_B);
+        if (debug & 2) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(slab_empty(s)); continue; }
+        uint32_t R[XB][4];   // all five loads in flight before the first store (one shared-memory latency per task)
 #pragma unroll
         for (int xb = 0; xb < XB; ++xb) ldsm_x4_trans(R[xb], slab + src_off[xb]);
 #pragma unroll
@@ -583,27 +582,50 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_
   } else {
     // ===================== writer: output planes -> NHWC =====================
     // matrix i = lane >> 3 holds the channel pair 2i, 2i+1 of each octet; its row r = lane & 7 is
-    // (channel 8*((r >> 1) & 1) + 2i + (r & 1), pixel block +2*(r >> 2)); task = (row, pixel blocks {xb0, xb0+2})
+    // (channel 8*((r >> 1) & 1) + 2i + (r & 1), pixel block +2*(r >> 2)); task = (row, pixel blocks {xb0, xb0+2}).
+    // Each lane ends up with the 16 contiguous NHWC bytes (8 channels) of one pixel; they go through a staging
+    // slice and out with one TMA store per two rows (ncu: scattered 32-byte runs straight from registers cost ~21 LSU wavefronts
+    // per STG.128, 28 % of the kernel's LSU traffic).
     const int ww = warp - (P_WARPS + 1);
     const int w_ch = 8 * ((lr >> 1) & 1) + 2 * lj + (lr & 1), w_pb = 2 * (lr >> 2);
     const int pb = 2 * (t >> 1), oct = t & 1;
+    const uint32_t stage_w = stage0 + ww * 2 * STAGE_B;
+    const uint32_t st_off = static_cast<uint32_t>(((pb * 8 + g) * CB + oct * 8) * 2);
     uint32_t n = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
       const TileCoord tc = decode_tile(tile, n_cblk, tiles_x, tiles_y);
       const uint32_t b = n % NBUF, k = n / NBUF;
       const uint32_t w_plane = plane_base(planes0 + b * PLANES_B, w_ch);
-      __nv_bfloat16* obase = out + ((static_cast<size_t>(tc.b) * H + tc.y0) * W + tc.x0 + pb * 8 + g) * C + tc.c0 + oct * 8;
       ptx::mbar_wait(out_full(b), k & 1u);
-#pragma unroll 4
-      for (int task = ww; task < TH * 2; task += W_WARPS) {
-        const int y = task >> 1, xb0 = task & 1;
-        uint32_t R[4];
-        ldsm_x4_trans(R, w_plane + y * ROW_B + (((xb0 + w_pb) ^ ((y >> 3) & 3)) << 4));
-        *reinterpret_cast<uint4*>(obase + (static_cast<size_t>(y) * W + xb0 * 8) * C) = make_uint4(R[0], R[1], R[2], R[3]);
+      if (debug & 4) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(planes_empty(b)); continue; }
+#pragma unroll 1
+      for (int r = 0; r < 4; ++r) {
+        const int ybase = (4 * ww + r) * STAGE_ROWS;
+        const uint32_t stage = stage_w + (r & 1) * STAGE_B;
+        uint32_t R[2 * STAGE_ROWS][4];
+#pragma unroll
+        for (int q = 0; q < 2 * STAGE_ROWS; ++q) {
+          const int y = ybase + (q >> 1), xb0 = q & 1;
+          ldsm_x4_trans(R[q], w_plane + y * ROW_B + (((xb0 + w_pb) ^ ((y >> 3) & 3)) << 4));
+        }
+        if (lane == 0) ptx::tma_store_wait_read<1>();   // the slice stored two rounds ago has left this staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 2 * STAGE_ROWS; ++q)   // dense box (a swizzled map pads 32-byte rows): the two pixel blocks of a lane quad share banks, 2-way
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + st_off + ((q >> 1) * TW + (q & 1) * 8) * CB * 2),
+                       "r"(R[q][0]), "r"(R[q][1]), "r"(R[q][2]), "r"(R[q][3])
+                       : "memory");
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tmap_out, tc.c0, tc.x0, tc.y0 + ybase, tc.b, stage);
+          ptx::tma_store_commit();
+        }
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(planes_empty(b));
     }
+    if (lane == 0) ptx::tma_store_wait<0>();
   }
 }
 }  // namespace r4
@@ -668,14 +690,17 @@ int launch_mma_r4(const void* in, const uint32_t* wtab, const float* bias, void*
   auto kfn = r4::dwconv7_mma_r4_kernel;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), r4::SMEM_B)) return rc;
   CUtensorMap ti;
-  if (int rc = make_tmap_nhwc(&ti, in, B, H, W, C, r4::IW, 2, r4::CB, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+  if (int rc = make_tmap_nhwc(&ti, in, B, H, W, C, r4::IW, r4::SROWS, r4::CB, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+  CUtensorMap to;
+  if (int rc = make_tmap_nhwc(&to, out, B, H, W, C, r4::TW, r4::STAGE_ROWS, r4::CB, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
   const int tiles_x = W / r4::TW, tiles_y = H / r4::TH, n_cblk = C / r4::CB;
   const long long total = static_cast<long long>(tiles_x) * tiles_y * n_cblk * B;
   FVLA_REQUIRE(total < (1ll << 31), "dwconv7_mma: too many tiles");
+  static const int dbg = std::getenv("FVLA_DW7_DEBUG") ? std::atoi(std::getenv("FVLA_DW7_DEBUG")) : 0;  // stage-skipping bits (timing only)
   const int resident = num_sms();   // one warp-specialised CTA per SM
   const int grid = total < resident ? static_cast<int>(total) : resident;
-  kfn<<<grid, r4::WS_THREADS, r4::SMEM_B, stream>>>(ti, wtab, bias, static_cast<__nv_bfloat16*>(out), H, W, C, tiles_x,
-                                             tiles_y, n_cblk, static_cast<int>(total));
+  kfn<<<grid, r4::WS_THREADS, r4::SMEM_B, stream>>>(ti, to, wtab, bias, H, W, C, tiles_x,
+                                             tiles_y, n_cblk, static_cast<int>(total), dbg);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
