@@ -428,7 +428,8 @@ def main() -> None:
             def kernel_of(label):
                 return ("ffn_fused_kernel" if "ffn_fused" in label else
                         "gemm_bf16_tcgen05_kernel" if "gemm" in label else
-                        "dwconv7_mma_kernel" if "dwconv k7 s1" in label else
+                        "dwconv7_mma_kernel" if ("dwconv k7 s1" in label and label.endswith("HW16")) else
+                        "dwconv7_mma_r4_kernel" if "dwconv k7 s1" in label else
                         "dwconv3_tma_kernel" if "dwconv k3 s1 m1" in label else
                         "dwconv7_s2m2_kernel" if "dwconv k7 s2" in label else
                         "attention_vis" if "vis.attention" in label else

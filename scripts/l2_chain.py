@@ -22,8 +22,9 @@ def run(chunk):
     hid = torch.empty(chunk, Hd, device="cuda", dtype=torch.float16)
     def step():
         for m0 in range(0, Mtot, chunk):
-            N.op_gemm(x[m0:m0 + chunk], w1, bias=b1, act=5, out=hid)
-            N.op_gemm(hid, w2, bias=b2, resid=res[m0:m0 + chunk], out=out[m0:m0 + chunk])
+            rows = min(chunk, Mtot - m0)
+            N.op_gemm(x[m0:m0 + rows], w1, bias=b1, act=5, out=hid[:rows])
+            N.op_gemm(hid[:rows], w2, bias=b2, resid=res[m0:m0 + rows], out=out[m0:m0 + rows])
     for _ in range(3):
         step()
     torch.cuda.synchronize()
@@ -36,5 +37,5 @@ def run(chunk):
     return e0.elapsed_time(e1) / 10
 
 
-for chunk in (131072, 65536, 32768, 16384, 8192):
+for chunk in (131072, 65536, 37888, 32768, 18944, 16384, 9472, 8192):
     print(f"chunk {chunk:7d} rows (hidden {chunk * Hd * 2 / 1e6:6.1f} MB): {run(chunk):.3f} ms per fc1+fc2 over {Mtot} rows")

@@ -58,11 +58,12 @@ def main() -> None:
                 fam["launches"] += k["n"]; fam["dram_bytes"] += k["rd"] + k["wr"]; fam["ms"] += k["ns"] / 1e6
         # per kernel (template instances merged): what bench.py reports as roofline_kernels[*].traffic
         kernels = {}
-        alias = {"gemm_bf16_tcgen05_kernel": "gemm_bf16_tcgen05_kernel", "ffn_fused_kernel": "ffn_fused_kernel",
-                 "dwconv7_mma_kernel": "dwconv7_mma_kernel", "dwconv3_tma_kernel": "dwconv3_tma_kernel",
+        alias = {"gemm_bf16_tcgen05_kernel": "gemm_bf16_tcgen05_kernel", "ffn_fused": "ffn_fused_kernel",
+                 "dwconv7_mma_r4_kernel": "dwconv7_mma_r4_kernel", "dwconv7_mma_kernel": "dwconv7_mma_kernel",
+                 "dwconv3_tma_kernel": "dwconv3_tma_kernel",
                  "dwconv7_s2m2": "dwconv7_s2m2_kernel", "stem_fused_kernel": "stem_fused_kernel",
-                 "attn_tc_kernel": "attention_vis", "flash_attn_v2_kernel": "attention_vis",
-                 "flash_attn_gqa_kernel": "attention_llm"}
+                 "attn_tc_causal_kernel": "attention_llm", "attn_tc_kernel": "attention_vis",
+                 "flash_attn_v2_kernel": "attention_vis", "flash_attn_gqa_kernel": "attention_llm"}
         for name, k in per.items():
             for pat, key in alias.items():
                 if pat in name:
