@@ -355,7 +355,9 @@ constexpr int BAR_B = 512;
 constexpr int P_WARPS = 3, W_WARPS = 4, M_WARPS = 16;            // + 1 TMA issuer; warpgroups: {P, P, P, issuer} {W x 4} {M x 16}
 constexpr int LIGHT_WARPS = P_WARPS + 1 + W_WARPS;
 constexpr int WS_THREADS = (LIGHT_WARPS + M_WARPS) * 32;
-constexpr int STAGE_ROWS = 2, STAGE_B = STAGE_ROWS * TW * CB * 2;  // writer staging slice: 2 rows x 32 px x 32 B of NHWC output, two per warp
+constexpr int STAGE_ROWS = 2;                                      // writer staging slice: 2 rows x 32 px x 32 B of NHWC output, two per warp,
+constexpr int STAGE_HALF = STAGE_ROWS * (TW / 2) * CB * 2 + 64;   // held as a left and a right 16-pixel half box, the right one skewed by
+constexpr int STAGE_B = 2 * STAGE_HALF;                            // 64 B so the two pixel blocks of a lane quad fall into different banks
 constexpr int SMEM_B = SLABS_B + NBUF * (PLANES_B + WTAB_B) + 2 * W_WARPS * STAGE_B + BAR_B + 1024;
 constexpr int LIGHT_REGS = 48, M_REGS = 96;                        // setmaxnreg: 768 threads launch with 80 registers each
 static_assert(LIGHT_WARPS % 4 == 0 && M_WARPS % 4 == 0, "setmaxnreg works on aligned groups of four warps");
@@ -590,7 +592,7 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
     const int w_ch = 8 * ((lr >> 1) & 1) + 2 * lj + (lr & 1), w_pb = 2 * (lr >> 2);
     const int pb = 2 * (t >> 1), oct = t & 1;
     const uint32_t stage_w = stage0 + ww * 2 * STAGE_B;
-    const uint32_t st_off = static_cast<uint32_t>(((pb * 8 + g) * CB + oct * 8) * 2);
+    const uint32_t st_off = static_cast<uint32_t>((t >> 1) * STAGE_HALF + (g * CB + oct * 8) * 2);
     uint32_t n = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
       const TileCoord tc = decode_tile(tile, n_cblk, tiles_x, tiles_y);
@@ -611,14 +613,15 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         if (lane == 0) ptx::tma_store_wait_read<1>();   // the slice stored two rounds ago has left this staging buffer
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 2 * STAGE_ROWS; ++q)   // dense box (a swizzled map pads 32-byte rows): the two pixel blocks of a lane quad share banks, 2-way
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + st_off + ((q >> 1) * TW + (q & 1) * 8) * CB * 2),
+        for (int q = 0; q < 2 * STAGE_ROWS; ++q)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + st_off + ((q >> 1) * (TW / 2) + (q & 1) * 8) * CB * 2),
                        "r"(R[q][0]), "r"(R[q][1]), "r"(R[q][2]), "r"(R[q][3])
                        : "memory");
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           tma_store_4d(&tmap_out, tc.c0, tc.x0, tc.y0 + ybase, tc.b, stage);
+          tma_store_4d(&tmap_out, tc.c0, tc.x0 + TW / 2, tc.y0 + ybase, tc.b, stage + STAGE_HALF);
           ptx::tma_store_commit();
         }
       }
@@ -692,7 +695,7 @@ int launch_mma_r4(const void* in, const uint32_t* wtab, const float* bias, void*
   CUtensorMap ti;
   if (int rc = make_tmap_nhwc(&ti, in, B, H, W, C, r4::IW, r4::SROWS, r4::CB, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
   CUtensorMap to;
-  if (int rc = make_tmap_nhwc(&to, out, B, H, W, C, r4::TW, r4::STAGE_ROWS, r4::CB, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  if (int rc = make_tmap_nhwc(&to, out, B, H, W, C, r4::TW / 2, r4::STAGE_ROWS, r4::CB, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
   const int tiles_x = W / r4::TW, tiles_y = H / r4::TH, n_cblk = C / r4::CB;
   const long long total = static_cast<long long>(tiles_x) * tiles_y * n_cblk * B;
   FVLA_REQUIRE(total < (1ll << 31), "dwconv7_mma: too many tiles");
