@@ -547,6 +547,22 @@ int dwconv(int dtype, const void* in, const float* w_packed, const float* bias, 
     }
     return dwconv7_mma(in, wtab, bias, out, B, H, W, Cin, stream);
   }
+  if (mma_on && dwconv7_s2m2_mma_supported(dtype, H, W, Cin, mult, ksize, stride, act)) {
+    if (wtab == nullptr) {   // op-level callers: build the table into a scratch buffer on the same stream
+      static uint32_t* scratch2 = nullptr;
+      static size_t scratch2_bytes = 0;
+      const size_t need = dwconv7_wtab_bytes(Cin);
+      if (need > scratch2_bytes) {
+        FVLA_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (scratch2 != nullptr) FVLA_CUDA_CHECK(cudaFree(scratch2));
+        FVLA_CUDA_CHECK(cudaMalloc(&scratch2, need));
+        scratch2_bytes = need;
+      }
+      if (int rc = dwconv7_s2m2_mma_prepare(w_packed, Cin, scratch2, stream)) return rc;
+      wtab = scratch2;
+    }
+    return dwconv7_s2m2_mma(in, wtab, bias, out, B, H, W, Cin, act, stream);
+  }
   const bool tma3_on = std::getenv("FVLA_DISABLE_DWCONV3_TMA") == nullptr;  // A/B switch, read per call (tests toggle it)
   if (tma3_on && dwconv3_tma_supported(dtype, H, W, Cin, mult, ksize, stride, act))
     return dwconv3_tma(in, w_packed, bias, out, B, H, W, Cin, stream);

@@ -355,9 +355,7 @@ constexpr int BAR_B = 512;
 constexpr int P_WARPS = 3, W_WARPS = 4, M_WARPS = 16;            // + 1 TMA issuer; warpgroups: {P, P, P, issuer} {W x 4} {M x 16}
 constexpr int LIGHT_WARPS = P_WARPS + 1 + W_WARPS;
 constexpr int WS_THREADS = (LIGHT_WARPS + M_WARPS) * 32;
-constexpr int STAGE_ROWS = 2;                                      // writer staging slice: 2 rows x 32 px x 32 B of NHWC output, two per warp,
-constexpr int STAGE_HALF = STAGE_ROWS * (TW / 2) * CB * 2 + 64;   // held as a left and a right 16-pixel half box, the right one skewed by
-constexpr int STAGE_B = 2 * STAGE_HALF;                            // 64 B so the two pixel blocks of a lane quad fall into different banks
+constexpr int STAGE_ROWS = 2, STAGE_B = STAGE_ROWS * TW * CB * 2;  // writer staging slice: 2 rows x 32 px x 32 B of NHWC output, two per warp
 constexpr int SMEM_B = SLABS_B + NBUF * (PLANES_B + WTAB_B) + 2 * W_WARPS * STAGE_B + BAR_B + 1024;
 constexpr int LIGHT_REGS = 48, M_REGS = 96;                        // setmaxnreg: 768 threads launch with 80 registers each
 static_assert(LIGHT_WARPS % 4 == 0 && M_WARPS % 4 == 0, "setmaxnreg works on aligned groups of four warps");
@@ -372,20 +370,123 @@ __device__ __forceinline__ int plane_row(int y) {
   const int q = y & 3;
   return q * 10 - (q == 3 ? 1 : 0) + (y >> 2);
 }
-__device__ __forceinline__ uint32_t plane_base(uint32_t planes, int ch) {
-  return planes + static_cast<uint32_t>(ch * PLANE_B + (ch >> 3) * OCTET_SKEW);
+__device__ __forceinline__ uint32_t plane_base(uint32_t planes, int ch, int skew = OCTET_SKEW) {
+  return planes + static_cast<uint32_t>(ch * PLANE_B + (ch >> 3) * skew);
 }
 
 struct TileCoord { int c0, x0, y0, b; };
-__device__ __forceinline__ TileCoord decode_tile(int id, int n_cblk, int tiles_x, int tiles_y) {
-  TileCoord tc;
+__device__ __forceinline__ TileCoord decode_tile(int id, int n_cblk, int tiles_x, int tiles_y, int tw = TW, int th = TH) {
+  TileCoord tc;   // x0 / y0 in OUTPUT pixels
   tc.c0 = (id % n_cblk) * CB;
   id /= n_cblk;
-  tc.x0 = (id % tiles_x) * TW;
+  tc.x0 = (id % tiles_x) * tw;
   id /= tiles_x;
-  tc.y0 = (id % tiles_y) * TH;
+  tc.y0 = (id % tiles_y) * th;
   tc.b = id / tiles_y;
   return tc;
+}
+
+// ---- stride 2, two output channels per input channel (FastViTHD PatchEmbed: ReparamLargeKernelConv 7x7 s2, groups = C,
+// 2C outputs, + GELU) on the same pipeline: the 38 x 40 x 16-channel input tile, its slabs and planes are those of the
+// stride-1 kernel; a tile produces 16 x 16 output pixels x 32 output channels (out channel = 2 * c + m).
+//   rows:    fragment row g owns output rows 2g, 2g+1 = input rows 4g + ky and 4g + 2 + ky: one x4 load of the A tiles
+//            (ky, xb), (ky+2, xb), (ky, xb+1), (ky+2, xb+1) is the whole A operand of kernel row ky;
+//   columns: output pixel n of an 8-pixel block reads input pixels 2n + kx: B[k][n] = w[ky][k - 2n], 21 inputs per block =
+//            one k16 step + one k8 step (whose A operand is the first register pair of the next block's quad);
+//   per channel 7 kernel rows x 2 blocks x 2 output channels x (k16 + k8) = 56 mma, 17 loads.
+constexpr int S2_TWO = 16, S2_THO = 16;                 // output tile
+constexpr int S2_OCB = 2 * CB;                          // output channels per tile
+constexpr int S2_SKEW = 32;                             // plane skew of input channels 8..15 (writer banks, see below)
+constexpr int S2_MOFF = S2_THO * ROW_B + 16;            // second output plane of an input channel, = 16 (mod 128) bytes
+constexpr int S2_WZERO = 56;                            // table word that is always zero
+constexpr int S2_STAGE_B = 2 * S2_TWO * S2_OCB * 2;     // writer staging slice: 2 rows x 16 px x 64 B
+static_assert(2 * S2_STAGE_B <= STAGE_B * 2 && S2_MOFF + S2_THO * ROW_B <= PLANE_B, "stride-2 buffers fit the stride-1 ones");
+
+__device__ __forceinline__ void mma_bf16_1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
+
+__device__ __forceinline__ void dw7_tensor_role_s2(uint32_t planes0, uint32_t wtab0, uint32_t bars,
+                                                   const float* __restrict__ bias, int n_cblk, int total_tiles,
+                                                   int act) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int lj = lane >> 3, lr = lane & 7;
+  auto planes_full = [&](uint32_t b) { return bars + 8u * (2 * NSLAB + b); };
+  auto out_full = [&](uint32_t b) { return bars + 8u * (2 * NSLAB + NBUF + b); };
+  auto wtab_full = [&](uint32_t b) { return bars + 8u * (2 * NSLAB + 3 * NBUF + b); };
+  const int ch = warp - LIGHT_WARPS;
+  // Toeplitz fragments: table word p of (m, ky) = taps (2p, 2p+1); this lane's pairs are p = t - g (k-lo), + 4 (k-hi), + 8 (k8 step)
+  uint32_t o[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int pq = t - g + 4 * q;
+    o[q] = static_cast<uint32_t>((pq >= 0 && pq <= 3) ? pq : -1);
+  }
+  // A quads of kernel row ky: lane address of matrix (lane >> 3): tile row class ky + 2 * (lj & 1), pixel block + (lj >> 1)
+  uint32_t a_off[7];
+#pragma unroll
+  for (int ky = 0; ky < 7; ++ky)
+    a_off[ky] = static_cast<uint32_t>((plane_row(ky + 2 * (lj & 1)) + lr) * ROW_B + (lj >> 1) * 16);
+  uint32_t n = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
+    const int c0 = (tile % n_cblk) * CB;
+    const uint32_t b = n % NBUF, k = n / NBUF;
+    const float bv0 = __ldg(bias + 2 * (c0 + ch)), bv1 = __ldg(bias + 2 * (c0 + ch) + 1);
+    const uint32_t plane = plane_base(planes0 + b * PLANES_B, ch, S2_SKEW);
+    const uint32_t wrow = wtab0 + b * WTAB_B + ch * (WTAB_WORDS * 4);
+    ptx::mbar_wait(wtab_full(b), k & 1u);
+    ptx::mbar_wait(planes_full(b), k & 1u);
+    float acc[2][2][4];   // [m][pixel block][fragment]
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[m][nb][e] = m ? bv1 : bv0;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+      uint32_t bw[2][3];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          bw[m][q] = lds32(wrow + ((o[q] == 0xffffffffu ? S2_WZERO : (m * 7 + ky) * 4 + static_cast<int>(o[q])) << 2));
+      uint32_t A0[4], A1[4], A2[2];
+      ldsm_x4(A0, plane + a_off[ky]);               // pixel blocks 0, 1
+      ldsm_x4(A1, plane + a_off[ky] + 32);          // pixel blocks 2, 3
+      asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];"
+                   : "=r"(A2[0]), "=r"(A2[1])
+                   : "r"(plane + a_off[ky] - (lj >> 1) * 16 + 64));   // pixel block 4 (lanes 0-15 address it)
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        mma_bf16_16816(acc[m][0], A0[0], A0[1], A0[2], A0[3], bw[m][0], bw[m][1]);
+        mma_bf16_1688(acc[m][0], A1[0], A1[1], bw[m][2]);
+        mma_bf16_16816(acc[m][1], A1[0], A1[1], A1[2], A1[3], bw[m][0], bw[m][1]);
+        mma_bf16_1688(acc[m][1], A2[0], A2[1], bw[m][2]);
+      }
+    }
+    // outputs (+ GELU) -> the channel's own plane: two 16 x 16 output planes, 80-byte rows, chunk ^ (row >> 3)
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        float v[4] = {acc[m][nb][0], acc[m][nb][1], acc[m][nb][2], acc[m][nb][3]};
+        if (act == ACT_GELU) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = gelu_tanh_fit(v[e]);
+        }
+        const uint32_t dst = plane + m * S2_MOFF + (2 * g) * ROW_B + ((nb ^ (g >> 2)) << 4) + t * 4;
+        sts32(dst, pack2(v[0], v[1]));
+        sts32(dst + ROW_B, pack2(v[2], v[3]));
+      }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(out_full(b));
+  }
 }
 
 // tensor-core role of the kernel below (one channel per warp); a function of its own so that it is compiled against
@@ -476,10 +577,13 @@ __device__ __forceinline__ void dw7_tensor_role(uint32_t planes0, uint32_t wtab0
   }
 }
 
+// S2 = false: stride 1 (debug = stage-skipping bits); S2 = true: stride 2 x 2 output channels (debug = activation)
+template <bool S2>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                       const uint32_t* __restrict__ wtab, const float* __restrict__ bias, int H, int W, int C,
                       int tiles_x, int tiles_y, int n_cblk, int total_tiles, int debug) {
+  constexpr int TWx = S2 ? S2_TWO : TW, THx = S2 ? S2_THO : TH, SC = S2 ? 2 : 1;
   extern __shared__ uint8_t smem_dwm[];
   const uint32_t base = (ptx::smem_u32(smem_dwm) + 1023u) & ~1023u;
   const uint32_t slabs = base;
@@ -517,7 +621,8 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 
   if (warp >= LIGHT_WARPS) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(M_REGS));
-    dw7_tensor_role(planes0, wtab0, bars, bias, n_cblk, total_tiles, debug);
+    if constexpr (S2) dw7_tensor_role_s2(planes0, wtab0, bars, bias, n_cblk, total_tiles, debug);
+    else dw7_tensor_role(planes0, wtab0, bars, bias, n_cblk, total_tiles, debug);
     return;
   }
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LIGHT_REGS));
@@ -526,7 +631,7 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
     if (lane == 0) {
       uint32_t n = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
-        const TileCoord tc = decode_tile(tile, n_cblk, tiles_x, tiles_y);
+        const TileCoord tc = decode_tile(tile, n_cblk, tiles_x, tiles_y, TWx, THx);
         const uint32_t b = n % NBUF, k = n / NBUF;
         ptx::mbar_wait(out_full(b), (k & 1u) ^ 1u);       // the tensor-core warps of tile n-3 are done with wtab[b]
         ptx::mbar_arrive_expect_tx(wtab_full(b), WTAB_B);
@@ -535,7 +640,7 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         for (int s = 0; s < NSLAB; ++s) {
           ptx::mbar_wait(slab_empty(s), (n & 1u) ^ 1u);
           ptx::mbar_arrive_expect_tx(slab_full(s), SLAB_B);
-          tma_load_4d(slabs + s * SLAB_B, &tmap_in, tc.c0, tc.x0 - 3, tc.y0 - 3 + SROWS * s, tc.b, slab_full(s));
+          tma_load_4d(slabs + s * SLAB_B, &tmap_in, tc.c0, SC * tc.x0 - 3, SC * tc.y0 - 3 + SROWS * s, tc.b, slab_full(s));
         }
       }
     }
@@ -551,7 +656,7 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       dst_off[xb] = static_cast<uint32_t>((xb * 4 + t) * 4);
     }
     const uint32_t ch_off0 = static_cast<uint32_t>(g * PLANE_B);
-    const uint32_t ch_off1 = static_cast<uint32_t>((8 + g) * PLANE_B + OCTET_SKEW);
+    const uint32_t ch_off1 = static_cast<uint32_t>((8 + g) * PLANE_B + (S2 ? S2_SKEW : OCTET_SKEW));
     uint32_t n = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
       const uint32_t b = n % NBUF, k = n / NBUF;
@@ -582,6 +687,52 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       if (lane == 0) ptx::mbar_arrive(planes_full(b));
     }
   } else {
+    if constexpr (S2) {
+      // ===================== writer, stride-2 kernel: 32 output channels, 64 bytes per pixel =====================
+      // matrix i = lane >> 3 holds the channel pair 2i, 2i+1 of each of the four octets: its row r is output channel
+      // co = 8 * (r >> 1) + 2i + (r & 1), i.e. plane (co >> 1), half (co & 1); lane (g, t) receives octet t of pixel g.
+      // Banks: planes step by 7 (mod 8) 16-byte units, the octet skew adds 2 per 8 input channels, the second output
+      // plane 1: the eight rows of a matrix land in eight different bank groups.
+      const int ww = warp - (P_WARPS + 1);
+      const int co = 8 * (lr >> 1) + 2 * lj + (lr & 1);
+      const uint32_t w_rel = static_cast<uint32_t>((co >> 1) * PLANE_B + ((co >> 4) & 1) * S2_SKEW + (co & 1) * S2_MOFF);
+      const uint32_t stage_w = stage0 + ww * 2 * STAGE_B;
+      const uint32_t st_off = static_cast<uint32_t>(g * 64 + t * 16);
+      uint32_t n = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
+        const TileCoord tc = decode_tile(tile, n_cblk, tiles_x, tiles_y, TWx, THx);
+        const uint32_t b = n % NBUF, k = n / NBUF;
+        const uint32_t w_plane = planes0 + b * PLANES_B + w_rel;
+        ptx::mbar_wait(out_full(b), k & 1u);
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+          const int ybase = 4 * ww + 2 * r;
+          const uint32_t stage = stage_w + (r & 1) * S2_STAGE_B;
+          uint32_t R[4][4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int y = ybase + (q >> 1), xb = q & 1;
+            ldsm_x4_trans(R[q], w_plane + y * ROW_B + ((xb ^ ((y >> 3) & 1)) << 4));
+          }
+          if (lane == 0) ptx::tma_store_wait_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + st_off + ((q >> 1) * S2_TWO + (q & 1) * 8) * 64),
+                         "r"(R[q][0]), "r"(R[q][1]), "r"(R[q][2]), "r"(R[q][3])
+                         : "memory");
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmap_out, 2 * tc.c0, tc.x0, tc.y0 + ybase, tc.b, stage);
+            ptx::tma_store_commit();
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(planes_empty(b));
+      }
+      if (lane == 0) ptx::tma_store_wait<0>();
+    } else {
     // ===================== writer: output planes -> NHWC =====================
     // matrix i = lane >> 3 holds the channel pair 2i, 2i+1 of each octet; its row r = lane & 7 is
     // (channel 8*((r >> 1) & 1) + 2i + (r & 1), pixel block +2*(r >> 2)); task = (row, pixel blocks {xb0, xb0+2}).
@@ -592,7 +743,7 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
     const int w_ch = 8 * ((lr >> 1) & 1) + 2 * lj + (lr & 1), w_pb = 2 * (lr >> 2);
     const int pb = 2 * (t >> 1), oct = t & 1;
     const uint32_t stage_w = stage0 + ww * 2 * STAGE_B;
-    const uint32_t st_off = static_cast<uint32_t>((t >> 1) * STAGE_HALF + (g * CB + oct * 8) * 2);
+    const uint32_t st_off = static_cast<uint32_t>(((pb * 8 + g) * CB + oct * 8) * 2);
     uint32_t n = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++n) {
       const TileCoord tc = decode_tile(tile, n_cblk, tiles_x, tiles_y);
@@ -613,15 +764,15 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         if (lane == 0) ptx::tma_store_wait_read<1>();   // the slice stored two rounds ago has left this staging buffer
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 2 * STAGE_ROWS; ++q)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + st_off + ((q >> 1) * (TW / 2) + (q & 1) * 8) * CB * 2),
+        for (int q = 0; q < 2 * STAGE_ROWS; ++q)   // dense box (TMA sources are 128-byte aligned, a swizzled map pads 32-byte rows): the two
+                                                   // pixel blocks of a lane quad are 512 B apart and share banks, 2-way
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + st_off + ((q >> 1) * TW + (q & 1) * 8) * CB * 2),
                        "r"(R[q][0]), "r"(R[q][1]), "r"(R[q][2]), "r"(R[q][3])
                        : "memory");
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           tma_store_4d(&tmap_out, tc.c0, tc.x0, tc.y0 + ybase, tc.b, stage);
-          tma_store_4d(&tmap_out, tc.c0, tc.x0 + TW / 2, tc.y0 + ybase, tc.b, stage + STAGE_HALF);
           ptx::tma_store_commit();
         }
       }
@@ -629,6 +780,7 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       if (lane == 0) ptx::mbar_arrive(planes_empty(b));
     }
     if (lane == 0) ptx::tma_store_wait<0>();
+    }
   }
 }
 }  // namespace r4
@@ -643,6 +795,23 @@ __global__ void dwconv7_wtab_kernel(const float* __restrict__ w, int C, uint32_t
     const int ky = j / 9, i = j % 9;
     const float lo = (i >= 1 && i <= 7) ? w[static_cast<size_t>(ky * 7 + i - 1) * C + c] : 0.0f;
     const float hi = (i <= 6) ? w[static_cast<size_t>(ky * 7 + i) * C + c] : 0.0f;
+    v = pack2(lo, hi);
+  }
+  wtab[idx] = v;
+}
+
+// stride-2 x2 table: word (m * 7 + ky) * 4 + p of input channel c = taps (2p, 2p+1) of kernel row ky of output channel
+// 2c + m as bf16 (tap 7 = 0); words 56..63 = 0
+__global__ void dwconv7_s2_wtab_kernel(const float* __restrict__ w, int C, uint32_t* __restrict__ wtab) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * WTAB_WORDS) return;
+  const int c = idx / WTAB_WORDS, j = idx % WTAB_WORDS;
+  uint32_t v = 0;
+  if (j < 56) {
+    const int p = j & 3, mk = j >> 2, m = mk / 7, ky = mk % 7;
+    const size_t co = static_cast<size_t>(2 * c + m), ld = static_cast<size_t>(2 * C);
+    const float lo = w[static_cast<size_t>(ky * 7 + 2 * p) * ld + co];
+    const float hi = (2 * p + 1 <= 6) ? w[static_cast<size_t>(ky * 7 + 2 * p + 1) * ld + co] : 0.0f;
     v = pack2(lo, hi);
   }
   wtab[idx] = v;
@@ -690,12 +859,12 @@ int launch_mma(const void* in, const uint32_t* wtab, const float* bias, void* ou
 
 int launch_mma_r4(const void* in, const uint32_t* wtab, const float* bias, void* out, int B, int H, int W, int C,
                   cudaStream_t stream) {
-  auto kfn = r4::dwconv7_mma_r4_kernel;
+  auto kfn = r4::dwconv7_mma_r4_kernel<false>;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), r4::SMEM_B)) return rc;
   CUtensorMap ti;
   if (int rc = make_tmap_nhwc(&ti, in, B, H, W, C, r4::IW, r4::SROWS, r4::CB, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
   CUtensorMap to;
-  if (int rc = make_tmap_nhwc(&to, out, B, H, W, C, r4::TW / 2, r4::STAGE_ROWS, r4::CB, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  if (int rc = make_tmap_nhwc(&to, out, B, H, W, C, r4::TW, r4::STAGE_ROWS, r4::CB, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
   const int tiles_x = W / r4::TW, tiles_y = H / r4::TH, n_cblk = C / r4::CB;
   const long long total = static_cast<long long>(tiles_x) * tiles_y * n_cblk * B;
   FVLA_REQUIRE(total < (1ll << 31), "dwconv7_mma: too many tiles");
@@ -708,7 +877,43 @@ int launch_mma_r4(const void* in, const uint32_t* wtab, const float* bias, void*
   return 0;
 }
 
+int launch_mma_s2(const void* in, const uint32_t* wtab, const float* bias, void* out, int B, int H, int W, int C, int act,
+                  cudaStream_t stream) {
+  auto kfn = r4::dwconv7_mma_r4_kernel<true>;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), r4::SMEM_B)) return rc;
+  CUtensorMap ti, to;
+  if (int rc = make_tmap_nhwc(&ti, in, B, H, W, C, r4::IW, r4::SROWS, r4::CB, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+  if (int rc = make_tmap_nhwc(&to, out, B, H / 2, W / 2, 2 * C, r4::S2_TWO, 2, r4::S2_OCB, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  const int tiles_x = (W / 2) / r4::S2_TWO, tiles_y = (H / 2) / r4::S2_THO, n_cblk = C / r4::CB;
+  const long long total = static_cast<long long>(tiles_x) * tiles_y * n_cblk * B;
+  FVLA_REQUIRE(total < (1ll << 31), "dwconv7_s2m2_mma: too many tiles");
+  const int resident = num_sms();
+  const int grid = total < resident ? static_cast<int>(total) : resident;
+  kfn<<<grid, r4::WS_THREADS, r4::SMEM_B, stream>>>(ti, to, wtab, bias, H, W, C, tiles_x, tiles_y, n_cblk,
+                                                   static_cast<int>(total), act);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
+
+bool dwconv7_s2m2_mma_supported(int dtype, int H, int W, int C, int mult, int k, int stride, int act) {
+  static const bool on = std::getenv("FVLA_DISABLE_DWCONV7_S2_MMA") == nullptr;  // A/B switch for profiling
+  return on && dtype == DT_BF16 && k == 7 && stride == 2 && mult == 2 && (act == ACT_NONE || act == ACT_GELU) &&
+         C % r4::CB == 0 && H % (2 * r4::S2_THO) == 0 && W % (2 * r4::S2_TWO) == 0;
+}
+
+int dwconv7_s2m2_mma_prepare(const float* w_packed, int C, uint32_t* wtab, cudaStream_t stream) {
+  const int n = C * WTAB_WORDS;
+  dwconv7_s2_wtab_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(w_packed, C, wtab);
+  FVLA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dwconv7_s2m2_mma(const void* in, const uint32_t* wtab, const float* bias, void* out, int B, int H, int W, int C,
+                     int act, cudaStream_t stream) {
+  return launch_mma_s2(in, wtab, bias, out, B, H, W, C, act, stream);
+}
 
 bool dwconv7_mma_supported(int dtype, int H, int W, int C, int mult, int k, int stride, int act) {
   return dtype == DT_BF16 && k == 7 && stride == 1 && mult == 1 && act == ACT_NONE && C % CB == 0 && H % TH == 0 &&

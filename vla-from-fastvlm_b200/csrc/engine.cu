@@ -284,6 +284,13 @@ int Engine::make_dw(DwW* d, const std::vector<float>& w, const std::vector<float
     weight_bytes += dwconv7_wtab_bytes(cin);
     d->wtab = static_cast<uint32_t*>(p);
     if (int rc = dwconv7_mma_prepare(d->w, cin, d->wtab, nullptr)) return rc;
+  } else if (cfg.dtype == FVLA_BF16 && k == 7 && stride == 2 && mult == 2 && cin % 16 == 0) {
+    void* p = nullptr;   // the stride-2 tensor-core path's table (dwconv() falls back by shape, the table is harmless then)
+    FVLA_CUDA_CHECK(cudaMalloc(&p, dwconv7_wtab_bytes(cin)));
+    dev_allocs_.push_back(p);
+    weight_bytes += dwconv7_wtab_bytes(cin);
+    d->wtab = static_cast<uint32_t*>(p);
+    if (int rc = dwconv7_s2m2_mma_prepare(d->w, cin, d->wtab, nullptr)) return rc;
   }
   return 0;
 }

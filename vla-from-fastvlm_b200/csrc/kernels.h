@@ -101,6 +101,12 @@ int dwconv_s2m2_tiled(const void* in, const float* w_packed, const float* bias, 
 bool dwconv7_mma_supported(int dtype, int H, int W, int C, int mult, int k, int stride, int act);
 size_t dwconv7_wtab_bytes(int C);
 int dwconv7_mma_prepare(const float* w_packed, int C, uint32_t* wtab, cudaStream_t stream);
+// 7x7 stride 2 with two output channels per input channel (+ optional GELU) on the same tensor-core pipeline; its
+// table (same size) comes from dwconv7_s2m2_mma_prepare
+bool dwconv7_s2m2_mma_supported(int dtype, int H, int W, int C, int mult, int k, int stride, int act);
+int dwconv7_s2m2_mma_prepare(const float* w_packed, int C, uint32_t* wtab, cudaStream_t stream);
+int dwconv7_s2m2_mma(const void* in, const uint32_t* wtab, const float* bias, void* out, int B, int H, int W, int C,
+                     int act, cudaStream_t stream);
 int dwconv7_mma(const void* in, const uint32_t* wtab, const float* bias, void* out, int B, int H, int W,
                 int C, cudaStream_t stream);
 
