@@ -26,6 +26,8 @@
 // bank groups.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "epilogue_math.cuh"
 #include "kernels.h"
@@ -43,8 +45,19 @@ constexpr int NSTAGE = 4;
 // CB = channels per tile.  8 x 32 pixels x 32 channels is the shape the engine's layers use; the 8 x 16 x 64 shape
 // (128-byte TMA rows, one pixel = one bank row) measured 10 % slower at 128^2 x 192 and only serves widths that are a
 // multiple of 16 but not of 32.
-template <int CB_> struct Geo {
+// R2 (CB = 32 only): TWO output rows per thread, 128-thread CTAs, three per SM.  ncu of the one-row kernel
+// (profiles/r02_ncu_full_dwconv3_tma_c192.txt): the LSU data pipe is 76 % busy and half of its shared-memory wavefronts
+// are the per-tile TAP loads — every quarter-warp re-reads the same 128 bytes, 20 LDS.128 per lane for 32 outputs.  With
+// two rows per thread the taps serve 64 outputs (56 instead of 76 LDS.128 per 64 outputs).  A thread's rows are two apart
+// (r, r+2) so that the two threads sharing a quarter-warp wavefront sit on ADJACENT rows, whose pitch is an odd
+// multiple of 64 B: conflict-free like the one-row mapping.
+template <int CB_, bool R2_ = false> struct Geo {
   static constexpr int CB = CB_;
+  static constexpr bool R2 = R2_;
+  static constexpr int WARPS = R2 ? 4 : CONSUMER_WARPS;
+  static constexpr int NTHREADS = WARPS * 32;
+  static constexpr int STAGES = R2 ? 3 : NSTAGE;
+  static constexpr int CTAS = R2 ? 3 : 2;
   static constexpr int NCV = CB / 8;                       // 16-byte channel vectors per pixel
   static constexpr int TW = CB == 32 ? 32 : 16;            // output pixels per tile row
   // CB 32: 64 B per pixel; one spare column makes the row pitch an ODD multiple of 64 B, so consecutive rows start
@@ -56,7 +69,7 @@ template <int CB_> struct Geo {
   static constexpr int SLOT_B = (TILE_B + 127) / 128 * 128;
   static constexpr int WSLOT_B = 10 * CB * 4;              // 9 tap rows + bias, fp32
   static constexpr int STAGE_B = SLOT_B + WSLOT_B;         // halo tile + its channel block's taps and bias
-  static constexpr int SMEM_B = NSTAGE * STAGE_B + 2 * NSTAGE * 8 + 1024;
+  static constexpr int SMEM_B = STAGES * STAGE_B + 2 * STAGES * 8 + 1024;
 };
 
 using epi::f32x2;
@@ -110,13 +123,14 @@ __device__ __forceinline__ void advance(TileIt& t, const TileIt& d, int n_cblk, 
 // its inputs, and thread 0 re-arms the slot one tile later.  Warps drift apart by up to NSTAGE - 1 tiles and there is
 // no CTA-wide barrier in the loop (ncu of the first version: 17 % of samples at a per-tile __syncthreads and 8 %
 // waiting for the weight LDG before its STS).
-template <int CB>
-__global__ void __launch_bounds__(THREADS, 2)
+template <int CB, bool R2>
+__global__ void __launch_bounds__(Geo<CB, R2>::NTHREADS, Geo<CB, R2>::CTAS)
 dwconv3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __restrict__ w,
                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int C,
                    int tiles_x, int tiles_y, int n_cblk, int total_tiles) {
-  using G = Geo<CB>;
-  constexpr int TW = G::TW, IW = G::IW, STAGE_B = G::STAGE_B, SLOT_B = G::SLOT_B;
+  using G = Geo<CB, R2>;
+  constexpr int TW = G::TW, IW = G::IW, STAGE_B = G::STAGE_B, SLOT_B = G::SLOT_B, NSTAGE = G::STAGES;
+  constexpr int NR = R2 ? 2 : 1;   // output rows per thread
   extern __shared__ uint8_t smem_dw3[];
   const uint32_t base = (ptx::smem_u32(smem_dw3) + 1023u) & ~1023u;
   const uint8_t* gbase = smem_dw3 + (base - ptx::smem_u32(smem_dw3));
@@ -130,7 +144,7 @@ dwconv3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __r
     ptx::prefetch_tmap(&tmap_in);
     for (int s = 0; s < NSTAGE; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), CONSUMER_WARPS);
+      ptx::mbar_init(empty_bar(s), G::WARPS);
     }
     ptx::fence_barrier_init();
   }
@@ -157,8 +171,9 @@ dwconv3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __r
   // CB 32: warp = 2 rows x 16 pixels, lane = (cv 0..3, row of the pair, pixel group): lanes 4..7 of a quarter-warp
   // read the next row.  CB 64: warp = 1 row x 16 pixels, lane = (cv 0..7, pixel group).  Either way the eight
   // 16-byte reads of an LDS.128 wavefront cover one whole 128-byte bank row.
+  // R2: warp = (4-row band, half of the 32 pixels), lane = (cv 0..3, row parity h, pixel group): rows band + h and band + h + 2.
   const int cv = lane % G::NCV;
-  const int row = CB == 32 ? (warp >> 1) * 2 + ((lane >> 2) & 1) : warp;
+  const int row = R2 ? (warp >> 1) * 4 + ((lane >> 2) & 1) : (CB == 32 ? (warp >> 1) * 2 + ((lane >> 2) & 1) : warp);
   const int px0 = CB == 32 ? (warp & 1) * 16 + (lane >> 3) * 4 : (lane >> 3) * 4;  // first of the lane's 4 output pixels
   // byte offset of this lane's first input (tile row `row`, pixel px0, channel vector cv) inside a slot
   const uint32_t lane_off = static_cast<uint32_t>((row * IW + px0) * G::PXB + cv * 16);
@@ -179,12 +194,12 @@ dwconv3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __r
     const uint32_t src = base + s * STAGE_B + lane_off;
     ptx::mbar_wait(full_bar(s), static_cast<uint32_t>(k / NSTAGE) & 1u);
 
-    f32x2 acc[4][4];
+    f32x2 acc[NR * 4][4];
     {
       const float4 b0 = *reinterpret_cast<const float4*>(wt + 9 * CB + cv * 8);
       const float4 b1 = *reinterpret_cast<const float4*>(wt + 9 * CB + cv * 8 + 4);
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
+      for (int o = 0; o < NR * 4; ++o) {
         acc[o][0] = pk2(b0.x, b0.y); acc[o][1] = pk2(b0.z, b0.w);
         acc[o][2] = pk2(b1.x, b1.y); acc[o][3] = pk2(b1.z, b1.w);
       }
@@ -200,11 +215,13 @@ dwconv3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __r
         wr[kx][2] = pk2(w1.x, w1.y); wr[kx][3] = pk2(w1.z, w1.w);
       }
 #pragma unroll
+      for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
       for (int i = 0; i < 6; ++i) {
         uint32_t x[4];
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
-                     : "r"(src + static_cast<uint32_t>((ky * IW + i) * G::PXB)));
+                     : "r"(src + static_cast<uint32_t>(((ky + 2 * rr) * IW + i) * G::PXB)));
         f32x2 xf[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) xf[c] = pk2(__uint_as_float(x[c] << 16), __uint_as_float(x[c] & 0xffff0000u));
@@ -213,7 +230,7 @@ dwconv3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __r
           const int kx = i - o;
           if (kx < 0 || kx >= 3) continue;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[o][c] = fma2(xf[c], wr[kx][c], acc[o][c]);
+          for (int c = 0; c < 4; ++c) acc[rr * 4 + o][c] = fma2(xf[c], wr[kx][c], acc[rr * 4 + o][c]);
         }
       }
     }
@@ -222,14 +239,16 @@ dwconv3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __r
     // ---- store: 4 pixels x 8 channels per lane, 16 bytes each ----
     __nv_bfloat16* orow = out + ((static_cast<size_t>(tc.b) * H + (tc.ty * TH + row)) * W + tc.tx * TW + px0) * C + tc.cb * CB + cv * 8;
 #pragma unroll
+    for (int rr = 0; rr < NR; ++rr)
+#pragma unroll
     for (int o = 0; o < 4; ++o) {
       uint4 v;
       float a, b2;
-      upk2(acc[o][0], a, b2); v.x = epi::pack_bf16(a, b2);
-      upk2(acc[o][1], a, b2); v.y = epi::pack_bf16(a, b2);
-      upk2(acc[o][2], a, b2); v.z = epi::pack_bf16(a, b2);
-      upk2(acc[o][3], a, b2); v.w = epi::pack_bf16(a, b2);
-      *reinterpret_cast<uint4*>(orow + static_cast<size_t>(o) * C) = v;
+      upk2(acc[rr * 4 + o][0], a, b2); v.x = epi::pack_bf16(a, b2);
+      upk2(acc[rr * 4 + o][1], a, b2); v.y = epi::pack_bf16(a, b2);
+      upk2(acc[rr * 4 + o][2], a, b2); v.z = epi::pack_bf16(a, b2);
+      upk2(acc[rr * 4 + o][3], a, b2); v.w = epi::pack_bf16(a, b2);
+      *reinterpret_cast<uint4*>(orow + (static_cast<size_t>(2 * rr) * W + o) * C) = v;
     }
   }
 }
@@ -256,20 +275,20 @@ int make_tmap(CUtensorMap* out, const void* ptr, int B, int H, int W, int C) {
   return 0;
 }
 
-template <int CB>
+template <int CB, bool R2>
 int launch(const void* in, const float* w_packed, const float* bias, void* out, int B, int H, int W, int C,
            cudaStream_t stream) {
-  using G = Geo<CB>;
-  auto kfn = dwconv3_tma_kernel<CB>;
+  using G = Geo<CB, R2>;
+  auto kfn = dwconv3_tma_kernel<CB, R2>;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), G::SMEM_B)) return rc;
   CUtensorMap ti;
   if (int rc = make_tmap<CB>(&ti, in, B, H, W, C)) return rc;
   const int tiles_x = W / G::TW, tiles_y = H / TH, n_cblk = C / CB;
   const long long total = static_cast<long long>(tiles_x) * tiles_y * n_cblk * B;
   FVLA_REQUIRE(total < (1ll << 31), "dwconv3_tma: too many tiles");
-  const int resident = 2 * num_sms();
+  const int resident = G::CTAS * num_sms();
   const int grid = total < resident ? static_cast<int>(total) : resident;
-  kfn<<<grid, THREADS, G::SMEM_B, stream>>>(ti, w_packed, bias, static_cast<__nv_bfloat16*>(out), H, W, C, tiles_x,
+  kfn<<<grid, G::NTHREADS, G::SMEM_B, stream>>>(ti, w_packed, bias, static_cast<__nv_bfloat16*>(out), H, W, C, tiles_x,
                                             tiles_y, n_cblk, static_cast<int>(total));
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -284,8 +303,11 @@ bool dwconv3_tma_supported(int dtype, int H, int W, int C, int mult, int k, int 
 
 int dwconv3_tma(const void* in, const float* w_packed, const float* bias, void* out, int B, int H, int W, int C,
                 cudaStream_t stream) {
-  if (W % Geo<32>::TW == 0) return launch<32>(in, w_packed, bias, out, B, H, W, C, stream);
-  return launch<64>(in, w_packed, bias, out, B, H, W, C, stream);
+  const bool r2 = std::getenv("FVLA_DWCONV3_ONE_ROW") == nullptr;  // A/B switch, read per call (tests toggle it)
+  if (W % Geo<32>::TW == 0)
+    return r2 ? launch<32, true>(in, w_packed, bias, out, B, H, W, C, stream)
+              : launch<32, false>(in, w_packed, bias, out, B, H, W, C, stream);
+  return launch<64, false>(in, w_packed, bias, out, B, H, W, C, stream);
 }
 
 }  // namespace fvla
