@@ -429,9 +429,8 @@ def main() -> None:
                 return ("ffn_fused_kernel" if "ffn_fused" in label else
                         "gemm_bf16_tcgen05_kernel" if "gemm" in label else
                         "dwconv7_mma_kernel" if ("dwconv k7 s1" in label and label.endswith("HW16")) else
-                        "dwconv7_mma_r4_kernel" if "dwconv k7 s1" in label else
+                        "dwconv7_mma_r4_kernel" if ("dwconv k7 s1" in label or "dwconv k7 s2" in label) else   # both strides
                         "dwconv3_tma_kernel" if "dwconv k3 s1 m1" in label else
-                        "dwconv7_s2m2_kernel" if "dwconv k7 s2" in label else
                         "attention_vis" if "vis.attention" in label else
                         "attention_llm" if "llm.attention" in label else
                         "stem_fused_kernel" if "stem_fused" in label else None)
