@@ -38,8 +38,7 @@ namespace fvla {
 namespace {
 
 constexpr int TH = 8;                 // output rows per tile
-constexpr int CONSUMER_WARPS = 8;
-constexpr int THREADS = CONSUMER_WARPS * 32;
+constexpr int CONSUMER_WARPS = 8;     // one-row kernel; the two-row kernel runs 4 warps (Geo::WARPS)
 constexpr int NSTAGE = 4;
 
 // CB = channels per tile.  8 x 32 pixels x 32 channels is the shape the engine's layers use; the 8 x 16 x 64 shape
