@@ -265,6 +265,56 @@ def test_dwconv3_tma(native, B, H, W, C, monkeypatch):
     assert not bool(o.any()), "impulse leaked outside its 3x3 neighbourhood"
 
 
+def test_dwconv3_one_and_two_row_kernels_agree(native, monkeypatch):
+    """The two-rows-per-thread 3x3 kernel (default) and the one-row kernel sum the same nine fp32 products in the same
+    order: their outputs are bit-identical (many tiles per CTA, several images, every channel-block count)."""
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    for (B, H, W, C) in [(3, 64, 64, 96), (2, 128, 128, 192), (1, 40, 96, 64)]:
+        x = torch.randn(B, H, W, C, generator=g).to(dev).bfloat16()
+        w = (torch.randn(C, 1, 3, 3, generator=g) / 3).to(dev)
+        b = torch.randn(C, generator=g).to(dev)
+        monkeypatch.delenv("FVLA_DWCONV3_ONE_ROW", raising=False)
+        two = native.op_dwconv(x, _pack_dw(w), b, 3, 1, 1, 0)
+        monkeypatch.setenv("FVLA_DWCONV3_ONE_ROW", "1")
+        one = native.op_dwconv(x, _pack_dw(w), b, 3, 1, 1, 0)
+        monkeypatch.delenv("FVLA_DWCONV3_ONE_ROW", raising=False)
+        assert torch.equal(one, two), (B, H, W, C)
+
+
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 16), (1, 64, 96, 48), (3, 128, 128, 96), (1, 256, 256, 96),
+                                     (2, 32, 64, 768)])
+def test_dwconv7_stride2_tensor_core(native, B, H, W, C, act):
+    """PatchEmbed depthwise 7x7, stride 2, two output channels per input channel (+ GELU) on the tensor-core pipeline
+    (stride-2 Toeplitz bands, k16 + k8 steps): single- and multi-tile grids, borders inside / between tiles and images,
+    per-channel distinct taps for both outputs of a channel; against conv2d with the taps it multiplies (bf16)."""
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 131 + H + 3 * W + C + act)
+    x = torch.randn(B, C, H, W, generator=g).to(dev)
+    w = (torch.randn(2 * C, 1, 7, 7, generator=g) / 7).to(dev)
+    b = torch.randn(2 * C, generator=g).to(dev)
+    xin = x.permute(0, 2, 3, 1).contiguous().bfloat16()
+    out = native.op_dwconv(xin, _pack_dw(w), b, 7, 2, 2, act)
+    assert out.shape == (B, H // 2, W // 2, 2 * C)
+
+    def ref_of(weights):
+        r = F.conv2d(xin.float().permute(0, 3, 1, 2), weights, b, stride=2, padding=3, groups=C)
+        return _act_ref(r, act).permute(0, 2, 3, 1)
+
+    _close(out, ref_of(w.bfloat16().float()), 1.0 / 128 if act == 0 else BF16_TOL, "dwconv7 s2 tensor core (bf16 taps)")
+    _close(out, ref_of(w), BF16_TOL, "dwconv7 s2 tensor core (fp32 taps)")
+    if act == 0:
+        # impulses at an even and an odd position read back every second tap of both output channels, exactly
+        for (py, px) in [(H // 2, W // 2), (H // 2 + 1, W // 2 - 1)]:
+            imp = torch.zeros(1, H, W, C, device=dev, dtype=torch.bfloat16)
+            imp[0, py, px, :] = 1.0
+            o = native.op_dwconv(imp, _pack_dw(w), torch.zeros(2 * C, device=dev), 7, 2, 2, 0).float()
+            want = F.conv2d(imp.float().permute(0, 3, 1, 2), w.bfloat16().float(), None, stride=2, padding=3,
+                            groups=C).permute(0, 2, 3, 1)
+            assert torch.equal(o, want), "stride-2 impulse response != taps"
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_stem_conv(native, dtype):
     dev = _dev()
