@@ -28,10 +28,20 @@ def run(chunk):
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+    # replay from a CUDA graph: the python/ctypes launch cost (~15 us per op) would otherwise dominate the small slices
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        step()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            step()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        gr.replay()
     e0.record()
     for _ in range(10):
-        step()
+        gr.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / 10
