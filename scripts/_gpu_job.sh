@@ -1,5 +1,9 @@
-for args in "2 64 96 7 1 1" "2 64 96 7 2 2" "2 64 96 3 1 1"; do
-  echo "== memcheck $args"; compute-sanitizer --tool memcheck --error-exitcode 3 python scripts/one_dwconv.py $args 2>&1 | tail -3
+set -x
+mkdir -p gpurun_out
+for b in 1 64; do
+  python scripts/profile_forward.py --batch $b --steps 5 --warmup 3 2>&1 | head -4 > gpurun_out/pdl_on_b$b.txt
+  FVLA_DISABLE_PDL=1 python scripts/profile_forward.py --batch $b --steps 5 --warmup 3 2>&1 | head -4 > gpurun_out/pdl_off_b$b.txt
 done
-echo "== racecheck 7 1 1"; timeout 300 compute-sanitizer --tool racecheck --error-exitcode 3 python scripts/one_dwconv.py 1 32 32 7 1 1 2>&1 | tail -4
-echo "== racecheck 7 2 2"; timeout 300 compute-sanitizer --tool racecheck --error-exitcode 3 python scripts/one_dwconv.py 1 32 32 7 2 2 2>&1 | tail -4
+head -4 gpurun_out/pdl_*.txt
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/t_gpu.log
+cat gpurun_out/t_gpu.log

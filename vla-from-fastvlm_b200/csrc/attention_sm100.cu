@@ -109,6 +109,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  pdl_sync();
 
   if (warp == 4) {
     // ===================== TMA producer =====================
@@ -331,6 +332,7 @@ attn_tc_causal_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  pdl_sync();
 
   if (warp == 4) {
     // ===================== TMA producer =====================
@@ -548,9 +550,8 @@ int attention_tc(const AttnArgs& a, cudaStream_t stream) {
     if (int rc = make_tmap_slice(&tk, a.k, rows, static_cast<long long>(a.heads_kv) * CHD, a.ld_qkv, 64u, AKV)) return rc;
     if (int rc = make_tmap_slice(&tv, a.v, rows, static_cast<long long>(a.heads_kv) * CHD, a.ld_qkv, 64u, AKV)) return rc;
     dim3 grid(ceil_div(a.N, CQ), a.heads_kv, a.B);
-    attn_tc_causal_kernel<<<grid, A_THREADS, C_SMEM, stream>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(a.o), a.ld_o,
-                                                             a.N, G, a.scale * 1.4426950408889634f);
-    FVLA_CUDA_CHECK(cudaGetLastError());
+    FVLA_CUDA_CHECK(launch_pdl(attn_tc_causal_kernel, grid, dim3(A_THREADS), C_SMEM, stream, tq, tk, tv,
+                               static_cast<__nv_bfloat16*>(a.o), a.ld_o, a.N, G, a.scale * 1.4426950408889634f));
     return 0;
   }
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_tc_kernel), A_SMEM)) return rc;
@@ -560,9 +561,9 @@ int attention_tc(const AttnArgs& a, cudaStream_t stream) {
   if (int rc = make_tmap_slice(&tk, a.k, rows, static_cast<long long>(a.heads_kv) * AHD, a.ld_qkv)) return rc;
   if (int rc = make_tmap_slice(&tv, a.v, rows, static_cast<long long>(a.heads_kv) * AHD, a.ld_qkv)) return rc;
   dim3 grid(a.N / AQ, a.heads_q, a.B);
-  attn_tc_kernel<<<grid, A_THREADS, A_SMEM, stream>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(a.o), a.ld_o, a.N,
-                                                      a.heads_q / a.heads_kv, a.scale * 1.4426950408889634f);
-  FVLA_CUDA_CHECK(cudaGetLastError());
+  FVLA_CUDA_CHECK(launch_pdl(attn_tc_kernel, grid, dim3(A_THREADS), A_SMEM, stream, tq, tk, tv,
+                             static_cast<__nv_bfloat16*>(a.o), a.ld_o, a.N, a.heads_q / a.heads_kv,
+                             a.scale * 1.4426950408889634f));
   return 0;
 }
 

@@ -2,6 +2,7 @@
 #include "engine.h"
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -13,6 +14,11 @@ namespace fvla {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 const char* last_error() { return g_error.c_str(); }
+
+bool pdl_enabled() {
+  static const bool on = std::getenv("FVLA_DISABLE_PDL") == nullptr;
+  return on;
+}
 
 int num_sms() {
   static int cached = 0;

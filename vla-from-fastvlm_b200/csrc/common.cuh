@@ -142,6 +142,20 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return r;
 }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------------
+// Every hot-path kernel is launched with the programmatic-stream-serialisation attribute (launch_pdl below): its
+// CTAs may become resident while the previous kernel of the stream drains, run their input-independent prologue
+// (barrier init, tensor-map prefetch, TMEM allocation, constant tables) and then block in pdl_sync() until the
+// previous grid has completed and its writes are visible.  ALL threads of a CTA execute pdl_sync() before the first
+// access to memory another kernel of the forward may have written, and before the first global write.  The trigger
+// follows the wait, so at most two grids are in flight and a CTA that triggers has already allocated its TMEM
+// (a dependent CTA can never take columns a still-unallocated primary CTA of the same SM waits for).
+// Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
@@ -149,5 +163,23 @@ int num_sms();  // cached SM count of the current device
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): raised once per pair (a process may hold
 // engines on several GPUs), thread-safe, ~50 ns on the repeat path
 int ensure_dyn_smem(const void* fn, int bytes);
+bool pdl_enabled();  // FVLA_DISABLE_PDL unset (A/B switch)
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-dependent-launch attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 
 }  // namespace fvla

@@ -41,6 +41,7 @@ constexpr int PRE_PX = 4;
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(128)
 preprocess_kernel(const TS* __restrict__ src, TD* __restrict__ dst, PreGeom g) {
+  pdl_sync();
   // grid (ceil(S / (128 * PRE_PX)), S, B): no index division
   const int xb = (static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x) * PRE_PX;
   const int y = static_cast<int>(blockIdx.y);
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(256)
 dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w,
               const float* __restrict__ bias, T* __restrict__ out, int B, int H, int W, int Cin,
               int Ho, int Wo, int act) {
+  pdl_sync();
   const int Cout = Cin * MULT;
   const int CV = Cout / 8, WG = (Wo + PX - 1) / PX;
   // 32-bit index arithmetic (the launcher checks the range): four 64-bit divisions per thread cost more than the
@@ -320,7 +322,7 @@ int launch_dwconv(const void* in, const float* w, const float* bias, void* out, 
   const int threads = 256;
   const long long blocks = ceil_div_ll(total, threads);
   FVLA_REQUIRE(total < (1ll << 32) - threads, "dwconv: too many work items for 32-bit indexing");
-  dwconv_kernel<T, K, STRIDE, MULT, PX><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+  (void)launch_pdl(dwconv_kernel<T, K, STRIDE, MULT, PX>, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, stream,
       static_cast<const T*>(in), w, bias, static_cast<T*>(out), B, H, W, Cin, Ho, Wo, act);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -346,6 +348,7 @@ int dwconv_dispatch(const void* in, const float* w, const float* bias, void* out
 template <typename T>
 __global__ void __launch_bounds__(256)
 se_mean_kernel(const T* __restrict__ x, float* __restrict__ mean, int HW, int C) {
+  pdl_sync();
   // grid (ceil(C/64), B); 256 threads = 8 channel vectors x 32 pixel lanes; pixels strided by 32
   __shared__ float part[32][65];
   const int cvl = threadIdx.x & 7, pl = threadIdx.x >> 3;
@@ -378,6 +381,7 @@ se_mean_kernel(const T* __restrict__ x, float* __restrict__ mean, int HW, int C)
 __global__ void __launch_bounds__(256)
 se_fc1_kernel(const float* __restrict__ mean, const float* __restrict__ w1, const float* __restrict__ b1,
               float* __restrict__ hidden, int B, int C, int Cr) {
+  pdl_sync();
   // one warp per (reduced channel r, sample b): a 3072-long dot product as 128-bit loads, 4 in flight per operand
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int r = blockIdx.x;
@@ -408,6 +412,7 @@ se_fc1_kernel(const float* __restrict__ mean, const float* __restrict__ w1, cons
 __global__ void __launch_bounds__(256)
 se_fc2_kernel(const float* __restrict__ hidden, const float* __restrict__ w2, const float* __restrict__ b2,
               float* __restrict__ gate, int B, int C, int Cr) {
+  pdl_sync();
   constexpr int MAXV = 8;  // Cr <= 256
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -431,6 +436,7 @@ se_fc2_kernel(const float* __restrict__ hidden, const float* __restrict__ w2, co
 template <typename T>
 __global__ void se_scale_gelu_kernel(const T* __restrict__ x, const float* __restrict__ gate,
                                      T* __restrict__ out, int HW, int C, long long total_vec) {
+  pdl_sync();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total_vec) return;
   const int CV = C / 8;
@@ -448,16 +454,16 @@ int se_gelu_t(const void* x, void* out, int B, int HW, int C, int Cr, const floa
               const float* b1, const float* w2, const float* b2, float* mean, float* gate,
               cudaStream_t s) {
   dim3 g1(ceil_div(C, 64), B);
-  se_mean_kernel<T><<<g1, 256, 0, s>>>(static_cast<const T*>(x), mean, HW, C);
+  (void)launch_pdl(se_mean_kernel<T>, g1, dim3(256), 0, s, static_cast<const T*>(x), mean, HW, C);
   // no extra scratch: fc1 writes the hidden vectors [B, Cr] into the gate buffer, fc2 reads them from there and
   // writes the gates [B, C] over the (now consumed) means, which the scale kernel then reads
   FVLA_REQUIRE(C % 4 == 0 && Cr <= 256 && Cr <= C, "se_gelu: channel counts out of range");
   float* hidden = gate;
   float* gates = mean;
-  se_fc1_kernel<<<dim3(Cr, ceil_div(B, 8)), 256, 0, s>>>(mean, w1, b1, hidden, B, C, Cr);
-  se_fc2_kernel<<<ceil_div(C, 8), 256, 0, s>>>(hidden, w2, b2, gates, B, C, Cr);
+  (void)launch_pdl(se_fc1_kernel, dim3(Cr, ceil_div(B, 8)), dim3(256), 0, s, mean, w1, b1, hidden, B, C, Cr);
+  (void)launch_pdl(se_fc2_kernel, dim3(ceil_div(C, 8)), dim3(256), 0, s, hidden, w2, b2, gates, B, C, Cr);
   const long long tv = static_cast<long long>(B) * HW * (C / 8);
-  se_scale_gelu_kernel<T><<<static_cast<unsigned>(ceil_div_ll(tv, 256)), 256, 0, s>>>(
+  (void)launch_pdl(se_scale_gelu_kernel<T>, dim3(static_cast<unsigned>(ceil_div_ll(tv, 256))), dim3(256), 0, s,
       static_cast<const T*>(x), gates, static_cast<T*>(out), HW, C, tv);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -467,7 +473,7 @@ template <typename TS, typename TD>
 int launch_pre(const PreprocessArgs& a, const PreGeom& g, cudaStream_t s) {
   FVLA_REQUIRE(a.S <= 65535 && a.B <= 65535, "preprocess: image side / batch exceed the launch grid");
   dim3 grid(static_cast<unsigned>(ceil_div(a.S, 128 * PRE_PX)), static_cast<unsigned>(a.S), static_cast<unsigned>(a.B));
-  preprocess_kernel<TS, TD><<<grid, 128, 0, s>>>(static_cast<const TS*>(a.src), static_cast<TD*>(a.dst), g);
+  (void)launch_pdl(preprocess_kernel<TS, TD>, grid, dim3(128), 0, s, static_cast<const TS*>(a.src), static_cast<TD*>(a.dst), g);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -148,6 +148,7 @@ dwconv3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const float* __r
     ptx::fence_barrier_init();
   }
   __syncthreads();
+  pdl_sync();
 
   const int first = blockIdx.x, stride = gridDim.x;
   const TileIt step = decode_tile(stride, n_cblk, tiles_x, tiles_y);
@@ -287,9 +288,9 @@ int launch(const void* in, const float* w_packed, const float* bias, void* out, 
   FVLA_REQUIRE(total < (1ll << 31), "dwconv3_tma: too many tiles");
   const int resident = G::CTAS * num_sms();
   const int grid = total < resident ? static_cast<int>(total) : resident;
-  kfn<<<grid, G::NTHREADS, G::SMEM_B, stream>>>(ti, w_packed, bias, static_cast<__nv_bfloat16*>(out), H, W, C, tiles_x,
-                                            tiles_y, n_cblk, static_cast<int>(total));
-  FVLA_CUDA_CHECK(cudaGetLastError());
+  FVLA_CUDA_CHECK(launch_pdl(kfn, dim3(grid), dim3(G::NTHREADS), G::SMEM_B, stream, ti, w_packed, bias,
+                             static_cast<__nv_bfloat16*>(out), H, W, C, tiles_x, tiles_y, n_cblk,
+                             static_cast<int>(total)));
   return 0;
 }
 

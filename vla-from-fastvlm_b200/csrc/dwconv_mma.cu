@@ -171,6 +171,7 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* 
     ptx::fence_barrier_init();
   }
   __syncthreads();
+  pdl_sync();
   if (tid == 0 && static_cast<int>(blockIdx.x) < total_tiles) {
     const TileCoord tc = decode_tile<NB>(blockIdx.x, n_cblk, tiles_x, tiles_y);
     ptx::mbar_arrive_expect_tx(wbar, G::WTAB_B);
@@ -618,6 +619,7 @@ dwconv7_mma_r4_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
     ptx::fence_barrier_init();
   }
   __syncthreads();
+  pdl_sync();
 
   if (warp >= LIGHT_WARPS) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(M_REGS));
@@ -851,9 +853,9 @@ int launch_mma(const void* in, const uint32_t* wtab, const float* bias, void* ou
   FVLA_REQUIRE(total < (1ll << 31), "dwconv7_mma: too many tiles");
   const int resident = 2 * num_sms();  // two CTAs per SM (shared memory), each walking a stride of tiles
   const int grid = total < resident ? static_cast<int>(total) : resident;
-  kfn<<<grid, THREADS, G::SMEM_B, stream>>>(ti, wtab, bias, static_cast<__nv_bfloat16*>(out), H, W, C, tiles_x,
-                                           tiles_y, n_cblk, static_cast<int>(total));
-  FVLA_CUDA_CHECK(cudaGetLastError());
+  FVLA_CUDA_CHECK(launch_pdl(kfn, dim3(grid), dim3(THREADS), G::SMEM_B, stream, ti, wtab, bias,
+                             static_cast<__nv_bfloat16*>(out), H, W, C, tiles_x, tiles_y, n_cblk,
+                             static_cast<int>(total)));
   return 0;
 }
 
@@ -871,9 +873,8 @@ int launch_mma_r4(const void* in, const uint32_t* wtab, const float* bias, void*
   static const int dbg = std::getenv("FVLA_DW7_DEBUG") ? std::atoi(std::getenv("FVLA_DW7_DEBUG")) : 0;  // stage-skipping bits (timing only)
   const int resident = num_sms();   // one warp-specialised CTA per SM
   const int grid = total < resident ? static_cast<int>(total) : resident;
-  kfn<<<grid, r4::WS_THREADS, r4::SMEM_B, stream>>>(ti, to, wtab, bias, H, W, C, tiles_x,
-                                             tiles_y, n_cblk, static_cast<int>(total), dbg);
-  FVLA_CUDA_CHECK(cudaGetLastError());
+  FVLA_CUDA_CHECK(launch_pdl(kfn, dim3(grid), dim3(r4::WS_THREADS), r4::SMEM_B, stream, ti, to, wtab, bias, H, W, C,
+                             tiles_x, tiles_y, n_cblk, static_cast<int>(total), dbg));
   return 0;
 }
 
@@ -889,9 +890,8 @@ int launch_mma_s2(const void* in, const uint32_t* wtab, const float* bias, void*
   FVLA_REQUIRE(total < (1ll << 31), "dwconv7_s2m2_mma: too many tiles");
   const int resident = num_sms();
   const int grid = total < resident ? static_cast<int>(total) : resident;
-  kfn<<<grid, r4::WS_THREADS, r4::SMEM_B, stream>>>(ti, to, wtab, bias, H, W, C, tiles_x, tiles_y, n_cblk,
-                                                   static_cast<int>(total), act);
-  FVLA_CUDA_CHECK(cudaGetLastError());
+  FVLA_CUDA_CHECK(launch_pdl(kfn, dim3(grid), dim3(r4::WS_THREADS), r4::SMEM_B, stream, ti, to, wtab, bias, H, W, C,
+                             tiles_x, tiles_y, n_cblk, static_cast<int>(total), act));
   return 0;
 }
 

@@ -146,6 +146,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  pdl_sync();  // prologue above (biases, barriers, TMEM) is input-independent
 
   if (warp_idx == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -586,6 +587,7 @@ ffn_fused_tmemh_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  pdl_sync();  // prologue above (biases, barriers, TMEM) is input-independent
 #ifdef FVLA_FFN_TRACE_BUILD
   // event log of the leader CTA of pair 0 (region 0: GEMM1 warp, 1: GEMM2 warp, 2: epilogue warp 4, 3: epilogue warp 12)
   const bool tr_on = p.trace != nullptr && blockIdx.x == 0 && lane_id() == 0;
@@ -914,8 +916,7 @@ int launch_ffn_tmemh(const FfnFusedArgs& a, cudaStream_t stream) {
   const int tiles = ceil_div(a.M, FPAIR_M);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kfn<<<grid, FFN_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw1, tw2, to, tr, p);
-  FVLA_CUDA_CHECK(cudaGetLastError());
+  FVLA_CUDA_CHECK(launch_pdl(kfn, dim3(grid), dim3(FFN_THREADS), Cfg::SMEM_BYTES, stream, tx, tw1, tw2, to, tr, p));
 #ifdef FVLA_FFN_TRACE_BUILD
   if (tr_now) {   // build with -DFVLA_FFN_TRACE_BUILD: event timeline of launch #10 on stderr
     static unsigned long long h[4 * 512];
@@ -948,8 +949,7 @@ int launch_ffn(const FfnFusedArgs& a, cudaStream_t stream) {
   const int tiles = ceil_div(a.M, FPAIR_M);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kfn<<<grid, FFN_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw1, tw2, to, p);
-  FVLA_CUDA_CHECK(cudaGetLastError());
+  FVLA_CUDA_CHECK(launch_pdl(kfn, dim3(grid), dim3(FFN_THREADS), Cfg::SMEM_BYTES, stream, tx, tw1, tw2, to, p));
   return 0;
 }
 

@@ -133,6 +133,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  pdl_sync();  // everything above is input-independent and overlaps the previous kernel's tail
 
   if (warp_idx == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -619,8 +620,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   ep.split_k = split;
   const long long work = static_cast<long long>(tiles) * split;
   const int grid = 2 * static_cast<int>(work < pairs ? work : pairs);
-  kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tw, td, ep);
-  FVLA_CUDA_CHECK(cudaGetLastError());
+  FVLA_CUDA_CHECK(launch_pdl(kfn, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tw, td, ep));
   return 0;
 }
 

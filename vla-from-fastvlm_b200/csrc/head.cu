@@ -82,6 +82,7 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   };
 
+  pdl_sync();
   // ---- LayerNorm(state) (eps 1e-5, biased variance); every CTA of the cluster needs all of it ----
   if (warp < R) {
     const int b = r0 + warp;
@@ -221,8 +222,8 @@ int launch_head(const HeadWeights& w, const float* pooled, const float* states, 
   const size_t smem = sizeof(float) * (static_cast<size_t>(R) * (w.H + w.Hd + 2 * w.F + w.S));
   FVLA_REQUIRE(smem <= 220 * 1024, "action head: hidden sizes too large for one CTA");
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kfn), static_cast<int>(smem))) return rc;
-  kfn<<<HEAD_CL * ceil_div(B, R), 256, smem, stream>>>(w, pooled, states, actions, state_feat, x1_scratch, fused, B);
-  FVLA_CUDA_CHECK(cudaGetLastError());
+  FVLA_CUDA_CHECK(launch_pdl(kfn, dim3(HEAD_CL * ceil_div(B, R)), dim3(256), smem, stream, w, pooled, states, actions,
+                             state_feat, x1_scratch, fused, B));
   return 0;
 }
 

@@ -47,6 +47,7 @@ template <typename TI, typename TO, int KEEP>
 __global__ void __launch_bounds__(128)
 rmsnorm_warp_kernel(const TI* __restrict__ x, const float* __restrict__ w, TO* __restrict__ out, int rows, int H,
                     float eps) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -129,9 +130,9 @@ void launch_rmsnorm(const void* x, const float* weight, void* out, int rows, int
   const TI* xi = static_cast<const TI*>(x);
   TO* oo = static_cast<TO*>(out);
   if (H <= 1024)
-    rmsnorm_warp_kernel<TI, TO, 4><<<ceil_div(rows, 4), 128, 0, stream>>>(xi, weight, oo, rows, H, eps);
+    (void)launch_pdl(rmsnorm_warp_kernel<TI, TO, 4>, dim3(ceil_div(rows, 4)), dim3(128), 0, stream, xi, weight, oo, rows, H, eps);
   else if (H <= 2048)
-    rmsnorm_warp_kernel<TI, TO, 8><<<ceil_div(rows, 4), 128, 0, stream>>>(xi, weight, oo, rows, H, eps);
+    (void)launch_pdl(rmsnorm_warp_kernel<TI, TO, 8>, dim3(ceil_div(rows, 4)), dim3(128), 0, stream, xi, weight, oo, rows, H, eps);
   else
     rmsnorm_kernel<TI, TO><<<rows, RMS_THREADS, 0, stream>>>(xi, weight, oo, H, eps);
 }
@@ -141,6 +142,7 @@ template <typename T, typename TO>
 __global__ void embed_splice_kernel(const T* __restrict__ table, const T* __restrict__ img,
                                     int n_img, const int* __restrict__ plan, TO* __restrict__ out,
                                     int T_len, int H) {
+  pdl_sync();
   const size_t pos = blockIdx.x;  // b*T + t
   const int b = static_cast<int>(pos / T_len);
   const int code = plan[pos];
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(256)
 pool_norm_kernel(const T* __restrict__ hidden, const float* __restrict__ w,
                  const int* __restrict__ pool_idx, const int* __restrict__ lens, int mode,
                  float* __restrict__ pooled, int T_len, int H, float eps) {
+  pdl_sync();
   __shared__ float red[32];
   const int b = blockIdx.x;
   float* dst = pooled + static_cast<size_t>(b) * H;
@@ -299,15 +302,15 @@ int embed_splice(int dtype, const void* table, const void* img_feats, int n_img,
                  void* out, int B, int T, int H, cudaStream_t stream, int out_f32) {
   FVLA_REQUIRE(H % 8 == 0 && B > 0 && T > 0, "embed_splice: H%8");
   if (dtype == DT_F32)
-    embed_splice_kernel<float, float><<<B * T, 128, 0, stream>>>(
+    (void)launch_pdl(embed_splice_kernel<float, float>, dim3(B * T), dim3(128), 0, stream,
         static_cast<const float*>(table), static_cast<const float*>(img_feats), n_img, plan,
         static_cast<float*>(out), T, H);
   else if (out_f32)
-    embed_splice_kernel<__nv_bfloat16, float><<<B * T, 128, 0, stream>>>(
+    (void)launch_pdl(embed_splice_kernel<__nv_bfloat16, float>, dim3(B * T), dim3(128), 0, stream,
         static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(img_feats),
         n_img, plan, static_cast<float*>(out), T, H);
   else
-    embed_splice_kernel<__nv_bfloat16, __nv_bfloat16><<<B * T, 128, 0, stream>>>(
+    (void)launch_pdl(embed_splice_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(B * T), dim3(128), 0, stream,
         static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(img_feats),
         n_img, plan, static_cast<__nv_bfloat16*>(out), T, H);
   FVLA_CUDA_CHECK(cudaGetLastError());
@@ -318,10 +321,10 @@ int pool_norm(int dtype, const void* hidden, const float* norm_w, const int* poo
               const int* lens, int mode, float* pooled, int B, int T, int H, float eps,
               cudaStream_t stream) {
   if (dtype == DT_F32)
-    pool_norm_kernel<float><<<B, 256, 0, stream>>>(static_cast<const float*>(hidden), norm_w,
+    (void)launch_pdl(pool_norm_kernel<float>, dim3(B), dim3(256), 0, stream, static_cast<const float*>(hidden), norm_w,
                                                    pool_idx, lens, mode, pooled, T, H, eps);
   else
-    pool_norm_kernel<__nv_bfloat16><<<B, 256, 0, stream>>>(
+    (void)launch_pdl(pool_norm_kernel<__nv_bfloat16>, dim3(B), dim3(256), 0, stream,
         static_cast<const __nv_bfloat16*>(hidden), norm_w, pool_idx, lens, mode, pooled, T, H, eps);
   FVLA_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -108,7 +108,6 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* _
     ptx::mbar_init(s_bar, 1);
     ptx::mbar_init(s_bar + 8u, 1);
     ptx::fence_barrier_init();
-    if (static_cast<int>(blockIdx.x) < total_tiles) request(blockIdx.x, 0);
   }
   for (int idx = tid; idx < 9 * (SF_CB / 2); idx += 256) {
     const int tap = idx / (SF_CB / 2), cp = idx % (SF_CB / 2);
@@ -133,6 +132,8 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_in, const uint32_t* _
     bias0[nb][1] = __ldg(b0_half + c0 + nb * 8 + 2 * t + 1);
   }
   __syncthreads();
+  pdl_sync();  // the weight staging above overlaps the previous kernel; the frames are its output
+  if (tid == 0 && static_cast<int>(blockIdx.x) < total_tiles) request(blockIdx.x, 0);
 
   int it = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -345,10 +346,8 @@ int stem_fused(const void* in, const uint32_t* btab, const float* b0_half, const
   // persistent CTAs: 4 per SM share the 3 channel blocks, each walking the tile list with a fixed channel block
   const int per_cb = std::max(1, (4 * num_sms()) / (C / SF_CB));
   dim3 grid(static_cast<unsigned>(total < per_cb ? total : per_cb), C / SF_CB, 1);
-  stem_fused_kernel<<<grid, 256, SF_SMEM, stream>>>(ti, btab, b0_half, w1_packed, b1,
-                                                    static_cast<__nv_bfloat16*>(out), S, C, tiles_per_img,
-                                                    static_cast<int>(total));
-  FVLA_CUDA_CHECK(cudaGetLastError());
+  FVLA_CUDA_CHECK(launch_pdl(stem_fused_kernel, grid, dim3(256), SF_SMEM, stream, ti, btab, b0_half, w1_packed, b1,
+                             static_cast<__nv_bfloat16*>(out), S, C, tiles_per_img, static_cast<int>(total)));
   return 0;
 }
 
