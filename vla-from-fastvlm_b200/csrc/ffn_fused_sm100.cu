@@ -587,6 +587,18 @@ ffn_fused_tmemh_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  // under the previous kernel's tail: the pairs share the (constant) weight panels out, one hidden chunk each, and
+  // pull them into L2 — at small M the weights are most of this launch's HBM traffic
+  if (warp_idx == 0 && lane == 0) {
+    for (int j = pair_id; j < nch; j += num_pairs) {
+#pragma unroll
+      for (int kp = 0; kp < Cfg::KP; ++kp)
+        ptx::tma_prefetch_2d(&tmap_w1, kp * 64, j * HC + static_cast<int>(cta_rank) * (HC / 2));
+#pragma unroll
+      for (int kb = 0; kb < HC / 64; ++kb)
+        ptx::tma_prefetch_2d(&tmap_w2, j * HC + kb * 64, static_cast<int>(cta_rank) * (C / 2));
+    }
+  }
   pdl_sync();  // prologue above (biases, barriers, TMEM) is input-independent
 #ifdef FVLA_FFN_TRACE_BUILD
   // event log of the leader CTA of pair 0 (region 0: GEMM1 warp, 1: GEMM2 warp, 2: epilogue warp 4, 3: epilogue warp 12)

@@ -133,6 +133,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  // Still under the previous kernel's tail: pull this CTA's half of the W panels of its FIRST work item into L2.  The
+  // weights are constants, so this needs no ordering against the previous grid; at small M (the b = 1 prefill) they
+  // are the whole HBM traffic of the launch and their DRAM round trip otherwise starts only after the wait.
+  if (warp_idx == 0 && lane == 0 && pair_id < num_tiles) {
+    const int tile = pair_id / p.split_k, ks = pair_id - tile * p.split_k;
+    const int n0 = (tile % num_n) * BLOCK_N + static_cast<int>(cta_rank) * Cfg::HALF_N;
+    const int kb_end = min(num_kb_all, (ks + 1) * kb_per);
+    for (int kb = ks * kb_per; kb < kb_end; ++kb) ptx::tma_prefetch_2d(&tmap_w, kb * BLOCK_K, n0);
+  }
   pdl_sync();  // everything above is input-independent and overlaps the previous kernel's tail
 
   if (warp_idx == 0) {

@@ -76,12 +76,34 @@ action_head_kernel(HeadWeights w, const float* __restrict__ pooled, const float*
   const int r0 = static_cast<int>(blockIdx.x / HEAD_CL) * R;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwarps = blockDim.x >> 5;
-  constexpr int NC = 4;
+  constexpr int NC = 8;   // weight rows in flight per warp
   auto cluster_sync = [] {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   };
 
+  // ---- under the previous kernel's tail: this CTA's slices of the two big matrices (constants) -> L2, so the
+  // latency-bound row streams below hit L2 instead of paying a DRAM round trip per step ----
+  {
+    const int fper0 = ((F + HEAD_CL - 1) / HEAD_CL + NC - 1) / NC * NC;
+    const int lo = crank * fper0, hi = min(F, lo + fper0);
+    if (hi > lo) {
+      const char* m0 = reinterpret_cast<const char*>(static_cast<const T*>(w.w_f0) + static_cast<size_t>(lo) * KC);
+      const char* m4 = reinterpret_cast<const char*>(static_cast<const T*>(w.w_f4) + static_cast<size_t>(lo) * F);
+      const size_t b0 = static_cast<size_t>(hi - lo) * KC * sizeof(T), b4 = static_cast<size_t>(hi - lo) * F * sizeof(T);
+      constexpr size_t CH = 4096;
+      const size_t n0c = (b0 + CH - 1) / CH, n4c = (b4 + CH - 1) / CH;
+      if (((reinterpret_cast<uintptr_t>(m0) | reinterpret_cast<uintptr_t>(m4) | b0 | b4) & 15u) == 0) {
+        for (size_t i = tid; i < n0c + n4c; i += blockDim.x) {
+          const bool second = i >= n0c;
+          const size_t off = (second ? i - n0c : i) * CH, tot = second ? b4 : b0;
+          const char* ptr = (second ? m4 : m0) + off;
+          const uint32_t bytes = static_cast<uint32_t>(tot - off < CH ? tot - off : CH);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+        }
+      }
+    }
+  }
   pdl_sync();
   // ---- LayerNorm(state) (eps 1e-5, biased variance); every CTA of the cluster needs all of it ----
   if (warp < R) {
