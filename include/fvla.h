@@ -160,7 +160,7 @@ int fvla_profile_report(fvla_engine* e, char* buf, int64_t buf_len);
  * transformers Qwen2MLP / Qwen2Attention projections]: D = act(rs*A W^T + bias) + resid.
  * `swiglu` is a flag word: bit 0 = SwiGLU epilogue over interleaved (gate, up) columns; bit 1 (bf16 path) = A and
  * W hold FP16 bits; bit 2 (bf16 path) = D is FP32 (the decoder's residual stream, ldd in fp32 elements) and resid,
- * if given, must be D itself (in-place update).  act 5 (bf16 path) = GELU of a pre-halved operand stored as FP16 (ConvFFN hidden tensor). */
+ * if given, must be D itself (in-place update); bits 8..15 = split-K factor of that in-place update (0/1 = none).  act 5 (bf16 path) = GELU of a pre-halved operand stored as FP16 (ConvFFN hidden tensor). */
 int fvla_op_gemm(int32_t dtype, const void* A, int32_t lda, const void* W, int32_t ldw, void* D,
                  int32_t ldd, int32_t M, int32_t N, int32_t K, const float* bias,
                  const float* row_scale, const void* resid, int32_t ldr, int32_t act,

@@ -169,6 +169,7 @@ int fvla_op_gemm(int32_t dtype, const void* A, int32_t lda, const void* W, int32
   g.M = M; g.N = N; g.K = K; g.bias = bias; g.row_scale = row_scale;
   g.resid = resid; g.ldr = ldr; g.act = act; g.swiglu = swiglu & 1; g.ab_f16 = (swiglu >> 1) & 1;
   g.out_f32 = (swiglu >> 2) & 1;
+  g.split_k = (swiglu >> 8) & 0xff;  // bits 8..15 of the flag word: split-K factor of the reduce-add epilogue (0 = none)
   g.block_n = block_n;
   return fvla::gemm(dtype, g, static_cast<cudaStream_t>(stream));
 }

@@ -705,8 +705,9 @@ int Engine::tap(int stage, const void* src, size_t bytes, size_t off, cudaStream
 // Forward
 // ---------------------------------------------------------------------------------------------
 int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, const void* resid,
-                     bool swiglu, cudaStream_t s, bool ab_f16, bool out_f32, bool rope, int split_k) {
+                     bool swiglu, cudaStream_t s, bool ab_f16, bool out_f32, bool rope, int split_k, int block_n) {
   GemmArgs g;
+  g.block_n = block_n;
   g.A = A; g.lda = w.K;
   g.W = w.w; g.ldw = w.K;
   g.D = D; g.ldd = swiglu ? w.N / 2 : w.N;
@@ -1153,7 +1154,7 @@ int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image
   // then moves 2.5x the bytes of the K = 896 GEMM's operands.  The norm kernel runs at 4.6 TB/s.
   static const bool fuse_on = std::getenv("FVLA_DISABLE_LAYER_FUSION") == nullptr;  // A/B switch for profiling
   const bool rope_fused = fuse_on && cfg.dtype == FVLA_BF16 && hd == 64 && Tm >= 32 && rope_tab_ != nullptr;
-  int split_o = 0, split_down = 0;
+  int split_o = 0, split_down = 0, bn_down = 0;
   if (fuse_on && cfg.dtype == FVLA_BF16) {
     const int pairs = num_sms() / 2;
     const int tiles = ceil_div(M, 256) * ceil_div(H, 64);   // small-M GEMMs run 64-wide tiles
@@ -1161,6 +1162,14 @@ int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image
     if (want >= 2) {
       split_o = std::min(want, std::max(1, (nq * hd) / 256));          // >= 4 k-blocks per split
       split_down = std::min(std::min(want, 8), std::max(1, cfg.intermediate / 256));
+      // long K: a 64-wide tile moves 16 KB of A per 4 KB of W through L2 -> SM for every k-block; 128-wide tiles with
+      // twice the splits keep the same number of busy pairs at 2/3 of the operand bytes (scripts/sweep_gemm_tiles.py,
+      // M 272 x N 896 x K 4864: 64/2 12.9 us, 64/4 11.7, 128/4 9.3, 256/8 9.9)
+      if (cfg.intermediate >= 2048 && H % 128 == 0) {
+        bn_down = 128;
+        const int tiles128 = ceil_div(M, 256) * ceil_div(H, 128);
+        split_down = std::min(std::min(std::max(2, pairs / std::max(1, tiles128)), 8), std::max(1, cfg.intermediate / 256));
+      }
     }
   }
   for (int l = 0; l < cfg.n_layers; ++l) {
@@ -1194,7 +1203,7 @@ int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image
     if (int rc = rmsnorm(cfg.dtype, X, L.ln2, Xn, M, H, cfg.rms_eps, s, stream32)) return rc;
     prof_end("llm.rmsnorm", 0.0, M * static_cast<double>(H) * (e + 4), s);
     if (int rc = run_gemm(L.gate_up, Xn, ACTB, M, ACT_NONE, nullptr, true, s)) return rc;
-    if (int rc = run_gemm(L.down, ACTB, X, M, ACT_NONE, X, false, s, false, true, false, split_down)) return rc;
+    if (int rc = run_gemm(L.down, ACTB, X, M, ACT_NONE, X, false, s, false, true, false, split_down, bn_down)) return rc;
     if (int rc = tap_stream(FVLA_TAP_LAYER0 + l)) return rc;
   }
   // ---- final norm + pooling ----

@@ -100,7 +100,8 @@ class Engine {
 
   // rope: rotate the q and k heads in the epilogue (qkv projection, head_dim 64); split_k: see GemmArgs
   int run_gemm(const GemmW& w, const void* A, void* D, int M, int act, const void* resid, bool swiglu,
-               cudaStream_t s, bool ab_f16 = false, bool out_f32 = false, bool rope = false, int split_k = 0);
+               cudaStream_t s, bool ab_f16 = false, bool out_f32 = false, bool rope = false, int split_k = 0,
+               int block_n = 0);
   int run_ffn(const VisBlock& blk, const void* z, void* hid, void* out_resid, int M, cudaStream_t s);
   int run_dw(const DwW& w, const void* in, void* out, int B, int H, int W, cudaStream_t s);
   int vision_chunk(const fvla_forward_args& a, int c0, int bc, void* feats, cudaStream_t s);

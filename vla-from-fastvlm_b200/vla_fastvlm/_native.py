@@ -217,7 +217,7 @@ def stream_ptr() -> int:
 def op_gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
             resid: Optional[torch.Tensor] = None, act: int = ACT_NONE, swiglu: bool = False,
             row_scale: Optional[torch.Tensor] = None, block_n: int = 0,
-            out: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, out_f32: bool = False, split_k: int = 0) -> torch.Tensor:
     """D = act(row_scale * A @ W^T + bias) + resid, A [M,K], W [N,K].
 
     bf16 operands with an fp32 `out` (or out_f32=True) and fp32 `resid`: the decoder's residual-stream epilogue.
@@ -241,7 +241,7 @@ def op_gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     check(load().fvla_op_gemm(code, ptr(a), K, ptr(w), K, ptr(out), out.stride(0), M, N,
                               K, ptr(bias), ptr(row_scale), ptr(resid),
                               resid.stride(0) if resid is not None else 0, act,
-                              int(swiglu) | (2 if ab_f16 else 0) | (4 if f32_stream else 0),
+                              int(swiglu) | (2 if ab_f16 else 0) | (4 if f32_stream else 0) | ((split_k & 0xff) << 8),
                               block_n, stream_ptr()), "fvla_op_gemm")
     return out
 
