@@ -1,3 +1,8 @@
-python scripts/profile_forward.py --batch 1 --steps 8 --warmup 3 2>&1 | head -3 | tail -1
-python scripts/profile_forward.py --batch 2 --steps 8 --warmup 3 2>&1 | head -3 | tail -1
-timeout 600 python -m pytest tests -m gpu -x -q -k "engine or fullsize or decoder_shapes or golden or plugin" 2>&1 | tail -3
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/t_gpu.log; cat gpurun_out/t_gpu.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; tail -c 300 gpurun_out/r02_bench_n1.json
+python scripts/profile_forward.py --batch 64 --steps 3 --warmup 2 > gpurun_out/r02_step_final_b64.txt 2>&1; head -4 gpurun_out/r02_step_final_b64.txt
+python scripts/profile_forward.py --batch 1 --steps 5 --warmup 3 > gpurun_out/r02_b1_profile.txt 2>&1; head -4 gpurun_out/r02_b1_profile.txt
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1700 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-default-config > gpurun_out/ncu_b.log 2>&1
+tail -2 gpurun_out/ncu_b.log | cut -c1-300

@@ -1,7 +1,7 @@
 """Tile-width / split-K sweep of the tcgen05 GEMM at the engine's small-M shapes (b = 1 prefill and one-image tower).
 Weights rotate over enough copies to exceed L2, as in a forward where every layer has its own.
 
-  python scripts/sweep_gemm_tiles.py > gpurun_out/sweep_gemm_tiles.txt
+  python scripts/sweep_gemm_tiles.py [--large] > gpurun_out/sweep_gemm_tiles.txt
 """
 import sys
 from pathlib import Path
@@ -15,6 +15,8 @@ L2 = 160e6
 
 
 def run(M, Nn, K, mode, bn, split=0, iters=48):
+    if M > 4096:
+        iters = 8
     f16 = mode in ("res16",)
     dt = torch.float16 if f16 else torch.bfloat16
     copies = max(2, min(64, int(L2 / (Nn * K * 2)) + 1))
@@ -66,6 +68,26 @@ SHAPES = [
     ("vis.s4.proj", 256, 1536, 1536, "res", [64, 128, 192, 256], [0]),
     ("proj.0", 256, 896, 3072, "gelu", [64, 128, 192, 256], [0]),
 ]
+LARGE = [
+    ("llm.qkv", 17408, 1152, 896, "", [128, 192, 256], [0]),
+    ("llm.o", 17408, 896, 896, "res32", [128, 192, 256], [0]),
+    ("llm.gate_up", 17408, 9728, 896, "swiglu", [128, 256], [0]),
+    ("llm.down", 17408, 896, 4864, "res32", [128, 192, 256], [0]),
+    ("vis.s2.fc1", 131072, 1536, 384, "gelu16", [128, 192, 256], [0]),
+    ("vis.s2.fc2", 131072, 384, 1536, "res16", [128, 192], [0]),
+    ("vis.s3.fc1", 32768, 3072, 768, "gelu16", [128, 192, 256], [0]),
+    ("vis.s3.fc2", 32768, 768, 3072, "res16", [128, 192, 256], [0]),
+    ("vis.s3.qkv", 32768, 2304, 768, "", [128, 192, 256], [0]),
+    ("vis.s3.proj", 32768, 768, 768, "res", [128, 192, 256], [0]),
+    ("vis.s4.fc1", 8192, 6144, 1536, "gelu16", [128, 192, 256], [0]),
+    ("vis.s4.fc2", 8192, 1536, 6144, "res16", [128, 192, 256], [0]),
+    ("vis.s4.qkv", 8192, 4608, 1536, "", [128, 192, 256], [0]),
+    ("vis.s4.proj", 8192, 1536, 1536, "res", [128, 192, 256], [0]),
+    ("proj.0", 16384, 896, 3072, "gelu", [128, 192, 256], [0]),
+    ("pe.pw", 524288, 192, 192, "gelu", [64, 128, 192], [0]),
+]
+if "--large" in sys.argv:   # the batch-64 shapes (vision chunks of 32 images)
+    SHAPES = LARGE
 for name, M, Nn, K, mode, bns, splits in SHAPES:
     auto = run(M, Nn, K, mode, 0, 0)
     res = []

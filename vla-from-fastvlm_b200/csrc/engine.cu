@@ -727,7 +727,7 @@ int Engine::run_gemm(const GemmW& w, const void* A, void* D, int M, int act, con
   }
   ++launches;
   const double fl = 2.0 * M * static_cast<double>(w.N) * w.K;
-  flops += fl;
+  flops += fl * flop_scale_;
   prof_begin(s);
   const int rc = gemm(cfg.dtype, g, s);
   if (profile_) {
@@ -1028,6 +1028,12 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
     Tm = std::max(Tm, mlen[b]);
   }
   merged_len = Tm;
+  {
+    double rows = 0.0, sq = 0.0;
+    for (int b = 0; b < B; ++b) { rows += mlen[b]; sq += static_cast<double>(mlen[b]) * mlen[b]; }
+    dec_row_frac_ = Tm > 0 ? rows / (static_cast<double>(B) * Tm) : 1.0;
+    dec_sq_frac_ = Tm > 0 ? sq / (static_cast<double>(B) * Tm * Tm) : 1.0;
+  }
   // Host staging of the splice plan: a ring of PINNED buffers, each guarded by an event, so the upload is a true
   // asynchronous copy (a pageable source above the driver's inline limit makes cudaMemcpyAsync stage + wait on the
   // host, which would serialise the caller's launch-ahead with the GPU).
@@ -1079,6 +1085,7 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
 // Kernel sequence of one forward; reads the splice plan / pool indices from the workspace (uploaded by forward()).
 // Pure stream-ordered launches (no allocation, no synchronisation): capturable into a CUDA graph.
 int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image, cudaStream_t s) {
+  flop_scale_ = 1.0;
   const int H = cfg.hidden, nimg = n_img_tokens();
   const size_t e = esz();
   int* d_plan = static_cast<int*>(ws_.bufs["plan"].first);
@@ -1172,6 +1179,7 @@ int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image
       }
     }
   }
+  flop_scale_ = dec_row_frac_;
   for (int l = 0; l < cfg.n_layers; ++l) {
     DecLayer& L = layers_[l];
     ++launches;
@@ -1192,7 +1200,7 @@ int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image
       prof_end("llm.rope", 0.0, 2.0 * M * static_cast<double>((nq + nkv) * hd) * e, s);
     }
     ++launches;
-    flops += 2.0 * B * static_cast<double>(Tm) * Tm * nq * hd;  // causal: half of 4*T^2*d
+    flops += 2.0 * B * static_cast<double>(Tm) * Tm * nq * hd * dec_sq_frac_;  // causal: half of 4*T^2*d, valid tokens
     prof_begin(s);
     if (int rc = attention(cfg.dtype, at, s)) return rc;
     prof_end("llm.attention T" + std::to_string(Tm), 2.0 * B * static_cast<double>(Tm) * Tm * nq * hd,
@@ -1206,6 +1214,7 @@ int Engine::launch_all(const fvla_forward_args& a, int B, int Tm, bool any_image
     if (int rc = run_gemm(L.down, ACTB, X, M, ACT_NONE, X, false, s, false, true, false, split_down, bn_down)) return rc;
     if (int rc = tap_stream(FVLA_TAP_LAYER0 + l)) return rc;
   }
+  flop_scale_ = 1.0;
   // ---- final norm + pooling ----
   float* pooled = static_cast<float*>(ws_.bufs["pooled"].first);
   ++launches;

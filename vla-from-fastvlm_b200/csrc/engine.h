@@ -136,6 +136,9 @@ class Engine {
   float* rope_cos_ = nullptr; float* rope_sin_ = nullptr; int rope_len_ = 0;
   uint32_t* rope_tab_ = nullptr;   // the same table as (cos, sin) fp16 pairs [pos][head_dim/2]: RoPE epilogue of the qkv GEMM
   int merged_T_ = 1;               // T' of the forward being launched (row -> position)
+  // algorithmic-work accounting of the decoder: valid rows / padded rows (and the same for squared lengths), so that
+  // `flops` counts the tokens of the ragged batch, not the B x T'max rows the GEMMs execute
+  double dec_row_frac_ = 1.0, dec_sq_frac_ = 1.0, flop_scale_ = 1.0;
   HeadWeights head_{};
   float* io_norm_ = nullptr;  // [S mean | S inv_std | A scale | A shift]
 
