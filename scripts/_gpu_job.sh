@@ -1,8 +1,3 @@
-set -x
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/t_gpu.log; cat gpurun_out/t_gpu.log
-python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; tail -c 300 gpurun_out/r02_bench_n1.json
-python scripts/profile_forward.py --batch 64 --steps 3 --warmup 2 > gpurun_out/r02_step_final_b64.txt 2>&1; head -4 gpurun_out/r02_step_final_b64.txt
-python scripts/profile_forward.py --batch 1 --steps 5 --warmup 3 > gpurun_out/r02_b1_profile.txt 2>&1; head -4 gpurun_out/r02_b1_profile.txt
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1700 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-default-config > gpurun_out/ncu_b.log 2>&1
-tail -2 gpurun_out/ncu_b.log | cut -c1-300
+for h in 0 3 7 2 0 3; do
+echo "hints $h"; FVLA_L2_HINTS=$h python scripts/profile_forward.py --batch 64 --steps 6 --warmup 3 2>&1 | grep -E "^# forward|N1536 K384 gelu|N384 K1536|k3 s1 m1 C384|k7 s1 m1 C384" | cut -c1-110
+done
