@@ -1,3 +1,5 @@
-for h in 0 3 7 2 0 3; do
-echo "hints $h"; FVLA_L2_HINTS=$h python scripts/profile_forward.py --batch 64 --steps 6 --warmup 3 2>&1 | grep -E "^# forward|N1536 K384 gelu|N384 K1536|k3 s1 m1 C384|k7 s1 m1 C384" | cut -c1-110
+timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "a_stationary or test_gemm_bf16 or fp16_hidden" 2>&1 | tail -5
+for i in 1 2; do
+python scripts/profile_forward.py --batch 64 --steps 6 --warmup 3 2>&1 | grep -E "^# forward|N1536 K384 gelu" | cut -c1-110
+FVLA_DISABLE_GEMM_AST=1 python scripts/profile_forward.py --batch 64 --steps 6 --warmup 3 2>&1 | grep -E "^# forward|N1536 K384 gelu" | cut -c1-110
 done
