@@ -284,7 +284,10 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])  # reference: a step = 8 CPU samples
     ap.add_argument("--model", default="fastvlm-0.5b")
-    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling) / global batch (strong scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch observations per GPU (the driver's contract); strong: ONE batch of --batch "
+                         "observations sharded over the ranks (BASELINE configs[1]: 'batch-sharded at 2/4/8')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-default-config", action="store_true", help="skip the fp32 default-configuration figures")
     ap.add_argument("--cpu-samples", type=int, default=64, help="samples timed for cpu_baseline (batches of 8, ~0.5 s/sample)")
@@ -293,11 +296,20 @@ def main() -> None:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    global_batch = args.batch * world
+    if args.scaling == "strong":   # one global batch, contiguous shards; per-rank sizes differ by at most one
+        global_batch = args.batch
+        lo, hi = shard_range(args.batch, rank, world)
+        if hi - lo < 1:
+            raise SystemExit(f"--scaling strong: batch {args.batch} leaves rank {rank} of {world} without work")
+        args.batch = hi - lo
     config = {"workload": f"FastVLA-{args.model.split('-')[-1]} bf16 batched select_action, batch {args.batch}/GPU synthetic "
                           "MetaWorld-MT50-shaped obs (480x480 frame -> 1024^2, 4-dim state, 8-16 token prompt, image tokens "
                           "prefixed: T'=256+T_text)",
-              "per_gpu_batch": args.batch, "global_batch": args.batch * world, "image": list(IMG_HW),
-              "model": args.model, "parallelism": f"dp{world} (batch sharded, no collective)",
+              "per_gpu_batch": args.batch, "global_batch": global_batch, "image": list(IMG_HW),
+              "model": args.model,
+              "parallelism": f"dp{world} (" + ("one global batch sharded over the ranks" if args.scaling == "strong"
+                                                else "batch sharded") + ", no collective)",
               "l2_policy": "inputs+weights per step (177 MB images + 1.25 GB weights) exceed the 126 MB L2"}
 
     # ------------------------------------------------------------ reference arm (CPU)
@@ -306,7 +318,7 @@ def main() -> None:
             return
         base, per = cpu_reference_run(args.model, 8 * max(1, args.steps), max(0, args.warmup))
         line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "impl": "reference",
                 "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -503,7 +515,7 @@ def main() -> None:
         if rank == 0 and not args.no_default_config:
             default_cfg = default_config_throughput(args.model, dev, frames_h[:16], states_h[:16], tasks[:16])
 
-    total = args.batch * world * args.steps
+    total = global_batch * args.steps
     value = total / (ms / 1e3)
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
@@ -511,7 +523,7 @@ def main() -> None:
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
                 "clocks": clocks,
                 "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "path": "pre-processor -> lerobot FastVLAPolicy.select_action(batch) -> post-processor, "
