@@ -1,17 +1,9 @@
-cd /root/repo
-cat > /tmp/tiny_fwd.py <<'PY'
-import sys, torch
-for p in ("/root/repo", "/root/repo/vla-from-fastvlm_b200", "/root/repo/tests", "/root/repo/tests/golden"):
-    sys.path.insert(0, p)
-from helpers import TINY_HEAD, make_engine, make_inputs, tiny_weights
-arch, sd, hsd = tiny_weights(0)
-eng = make_engine(arch, sd, hsd, torch.bfloat16)
-for B in (1, 5):
-    images, states, ids, mask = make_inputs(B, 120, 160, 9, arch.text.vocab, TINY_HEAD["state_dim"], seed=3, image_mode="prefix")
-    for _ in range(3):
-        out = eng.forward(images.to(eng.device), ids, mask.sum(1), states=states.to(eng.device))
-    torch.cuda.synchronize()
-    print(B, out.float().abs().mean().item())
-PY
-echo "== memcheck"; timeout 400 compute-sanitizer --tool memcheck --error-exitcode 3 python /tmp/tiny_fwd.py 2>&1 | tail -6
-echo "== synccheck"; timeout 300 compute-sanitizer --tool synccheck --error-exitcode 3 python /tmp/tiny_fwd.py 2>&1 | tail -4
+L=vla-from-fastvlm_b200/vla_fastvlm/_lib/libfvla.so
+cp $L /tmp/base.so
+for i in 1 2; do
+cp /tmp/base.so $L
+echo base; for b in 1 64; do python scripts/profile_forward.py --batch $b --steps 8 --warmup 3 2>&1 | grep "^# forward"; done
+cp vla-from-fastvlm_b200/csrc/build_early/libfvla_early.so $L
+echo early; for b in 1 64; do python scripts/profile_forward.py --batch $b --steps 8 --warmup 3 2>&1 | grep "^# forward"; done
+done
+timeout 300 python -m pytest tests -m gpu -x -q -k "pdl or engine" 2>&1 | tail -2
