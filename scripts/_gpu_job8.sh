@@ -1,6 +1,5 @@
 set -x
 N=$1
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err
-tail -c 400 gpurun_out/r02_bench_n$N.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 scripts/bench_train.py --steps 20 --warmup 5 > gpurun_out/r02_train_1p5b_n$N.json 2> gpurun_out/r02_train_n$N.err
-tail -c 600 gpurun_out/r02_train_1p5b_n$N.json
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 --no-default-config > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err
+grep '^{' gpurun_out/r02_bench_n$N.json | tail -c 300
