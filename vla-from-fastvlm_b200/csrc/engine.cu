@@ -665,8 +665,6 @@ int Engine::ensure(const std::string& name, size_t bytes, void** out) {
   bytes = (bytes + 255) & ~static_cast<size_t>(255);
   auto it = ws_.bufs.find(name);
   if (it != ws_.bufs.end() && it->second.second >= bytes) { *out = it->second.first; return 0; }
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  (void)cs;
   if (it != ws_.bufs.end()) {
     FVLA_CUDA_CHECK(cudaDeviceSynchronize());
     FVLA_CUDA_CHECK(cudaFree(it->second.first));
@@ -1007,7 +1005,7 @@ int Engine::forward(const fvla_forward_args& a, cudaStream_t s) {
   FVLA_REQUIRE(finalized_, "forward before finalize");
   FVLA_REQUIRE(a.batch > 0 && a.n_tokens > 0, "forward: empty batch");
   FVLA_REQUIRE(a.token_ids != nullptr && a.text_len != nullptr, "forward: token_ids/text_len required");
-  const int B = a.batch, T = a.n_tokens, H = cfg.hidden, nimg = n_img_tokens();
+  const int B = a.batch, T = a.n_tokens, nimg = n_img_tokens();
   const size_t e = esz();
   launches = 0;
   flops = 0.0;

@@ -31,7 +31,9 @@
 namespace fvla {
 namespace {
 using namespace epi;
+#ifdef FVLA_FFN_TRACE_BUILD
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+#endif
 
 constexpr int FM = 128;            // rows per CTA
 constexpr int FPAIR_M = 256;       // rows per CTA pair
