@@ -970,10 +970,12 @@ int launch_ffn(const FfnFusedArgs& a, cudaStream_t stream) {
 }  // namespace
 
 bool ffn_fused_supported(int dtype, int C, int hidden) {
+  if (ffn_wide_supported(dtype, C, hidden)) return true;
   return dtype == DT_BF16 && (C == 96 || C == 192) && hidden % HC == 0 && hidden >= HC && hidden <= 4 * C;
 }
 
 int ffn_fused(const FfnFusedArgs& a, cudaStream_t stream) {
+  if (a.C == 384) return ffn_wide(a, stream);
   FVLA_REQUIRE(a.M > 0 && ffn_fused_supported(DT_BF16, a.C, a.hidden), "ffn_fused: unsupported shape");
   FVLA_REQUIRE(a.b1 != nullptr && a.b2 != nullptr && a.resid != nullptr, "ffn_fused: biases and residual required");
   static const bool smem_h = std::getenv("FVLA_FFN_SMEM_H") != nullptr;    // A/B switches for profiling

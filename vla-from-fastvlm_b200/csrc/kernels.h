@@ -55,6 +55,10 @@ struct FfnFusedArgs {
 };
 bool ffn_fused_supported(int dtype, int C, int hidden);
 int ffn_fused(const FfnFusedArgs& a, cudaStream_t stream);
+// C = 384 (stage 2): 64-wide hidden chunks, H double-buffered in tensor memory (ffn_wide_sm100.cu); reached through
+// ffn_fused / ffn_fused_supported, opt-in by FVLA_ENABLE_FFN_WIDE
+bool ffn_wide_supported(int dtype, int C, int hidden);
+int ffn_wide(const FfnFusedArgs& a, cudaStream_t stream);
 
 // ---- image ingest ----------------------------------------------------------------------------
 struct PreprocessArgs {
